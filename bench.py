@@ -1,0 +1,421 @@
+#!/usr/bin/env python3
+"""bench.py -- sfft_exec throughput on B200 (BASELINE.json metric), one JSON line.
+
+A "step" is one sparse-FFT transform of one synthetic k-sparse signal per GPU (one
+pass of the hot path: Comb pre-filter, permuted windowed gather, bucket FFTs,
+top-2k selection, voting, median estimation).  Default workload = BASELINE.json
+configs[1]: sFFT v2, n = 2^24, k = 1000, exact k-sparse, 1 B200.
+
+  value : Gsamples/s = (signals * n) / time, inputs resident in HBM, result left as a
+          sparse (loc, val) list in HBM; CUDA events on the launching stream.
+  e2e   : same metric through the legacy C-ABI call sfft_exec(plan, in, out) with
+          HOST buffers: H2D of the signal + transform + dense out + D2H inside the
+          timed region.
+  roofline / cpu_baseline : see DESIGN.md "Measurement".
+
+N > 1 (torchrun): every rank transforms its own signals (sfft_exec_many-style
+partition, no data-path collective), weak scaling, max-over-ranks timing.
+
+`--impl reference` times the reference's own CPU implementation (oracle/_ref: the
+unmodified reference sources compiled over the FFTW shim) on the host cores.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+WORKLOADS = {
+    # name: (version, n, k, noisy_snr_db or None, description)
+    "C1": (1, 1 << 22, 50, None, "sFFT v1 exact k-sparse n=2^22 k=50"),
+    "C2": (2, 1 << 24, 1000, None, "sFFT v2 (Comb) exact k-sparse n=2^24 k=1000"),
+    "C3": (3, 1 << 26, 2000, None, "sFFT v3 exact-sparse n=2^26 k=2000"),
+    "C4": (1, 1 << 27, 500, 20.0, "sFFT v1 noisy 20 dB n=2^27 k=500"),
+    "C5": (1, 1 << 20, 100, None, "sFFT v1 n=2^20 k=100 batch"),
+}
+
+
+def env_int(name, default):
+    try:
+        return int(os.environ.get(name, default))
+    except ValueError:
+        return default
+
+
+# --------------------------------------------------------------------------- #
+# clocks sampling (B200_PROFILING.md recipe)
+# --------------------------------------------------------------------------- #
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+             "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu = gpu_index
+        self.samples = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(self.gpu), f"--query-gpu={self.QUERY}",
+                 "--format=csv,noheader,nounits", "-lms", "100"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.samples.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for s in self.samples:
+            f = [t.strip() for t in s.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                smax.append(float(f[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None,
+                "sm_max_mhz": max(smax) if smax else None,
+                "samples": len(sm), "reasons": sorted(reasons)}
+
+
+# --------------------------------------------------------------------------- #
+# reference arm: the reference's CPU path on the host cores
+# --------------------------------------------------------------------------- #
+def cpu_reference_run(workload, nsig, steps, warmup, budget_s=150.0):
+    """Times sfft_exec / sfft_exec_many of the compiled reference (oracle/_ref fast
+    build = the reference's own optimisation flags).  Returns a dict."""
+    import numpy as np
+    from oracle import ref
+
+    version, n, k, snr_db, desc = WORKLOADS[workload]
+    kind = "fast" if ref.available("fast") else "parity"
+    if not ref.available(kind):
+        return {"unavailable": "oracle/_ref not built (needs the reference sources at build time)"}
+    cores = min(nsig, os.cpu_count() or 1)
+    L = ref.lib(kind)
+    t0 = time.time()
+    plan = ref.RefPlan(n, k, version, kind=kind, threads=cores)
+    plan_s = time.time() - t0
+    xs = []
+    for i in range(nsig):
+        x, _ = ref.generate_input(n, k, 1000 + i, kind=kind)
+        xs.append(x)
+    if snr_db is not None:
+        import math
+        std = math.sqrt(k / (2.0 * 10 ** (snr_db / 10.0)))
+        for x in xs:
+            L.ref_awgn(x.ctypes.data, n, std)
+
+    def one():
+        plan.seed(17, 4711)
+        t = time.perf_counter()
+        if nsig == 1:
+            plan.exec(xs[0])
+        else:
+            plan.exec_many(xs)
+        return time.perf_counter() - t
+
+    first = one()                       # also serves as the only warm-up we can afford
+    per_step = first
+    fit = int(max(1, min(steps, (budget_s - first) // max(per_step, 1e-9))))
+    times = []
+    if warmup <= 0 or first * (fit + 1) > budget_s:
+        times.append(first)
+        fit -= 1
+    for _ in range(max(0, fit)):
+        times.append(one())
+    total = sum(times)
+    value = nsig * n * len(times) / total / 1e9
+    return {
+        "value": value, "unit": "Gsamples/s", "cores": cores, "kind": "reference",
+        "sample": (f"{len(times)} full sfft_exec{'_many' if nsig > 1 else ''} call(s) of {desc}, "
+                   f"{nsig} signal(s), reference sources built -O3 -ffast-math -march=x86-64-v3 "
+                   f"-fopenmp -DNDEBUG over the oracle's radix-2 FFT shim (FFTW is not installable); "
+                   f"plan build {plan_s:.1f}s excluded"),
+        "steps_timed": len(times), "ms_per_step": 1e3 * total / len(times),
+        "cpu_model": _cpu_model(),
+    }
+
+
+def _cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except Exception:
+        pass
+    return "unknown"
+
+
+def run_reference_arm(args):
+    rank = env_int("RANK", 0)
+    if rank != 0:
+        return
+    r = cpu_reference_run(args.workload, args.gpus, args.steps, args.warmup)
+    version, n, k, snr_db, desc = WORKLOADS[args.workload]
+    if "unavailable" in r:
+        print(json.dumps({"impl": "reference", "unavailable": r["unavailable"]}))
+        return
+    line = {
+        "metric": "sfft_exec throughput", "value": r["value"], "unit": "Gsamples/s",
+        "n_gpus": args.gpus, "steps": r["steps_timed"], "steps_requested": args.steps,
+        "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "impl": "reference",
+        "config": {"workload": f"{args.workload}: {desc}", "signals_per_step": args.gpus,
+                   "n": n, "k": k, "version": version},
+        "cpu_baseline": {"value": r["value"], "unit": "Gsamples/s", "cores": r["cores"],
+                         "kind": r["kind"], "sample": r["sample"], "cpu_model": r["cpu_model"]},
+        "e2e": {"value": r["value"], "unit": "Gsamples/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------- #
+# our arm
+# --------------------------------------------------------------------------- #
+def synth_signals(torch, n, k, count, seed, snr_db, device):
+    """k unit spikes at random locations -> x = unnormalised inverse DFT (the
+    reference's generator, src/simulation.cc:104-111, with torch's RNG/FFT for speed;
+    synthesis is outside every timed region)."""
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    out = []
+    for i in range(count):
+        loc = torch.randint(0, n, (k,), generator=g)
+        xf = torch.zeros(n, dtype=torch.complex128, device=device)
+        xf[loc.to(device)] = 1.0
+        x = torch.fft.ifft(xf) * n
+        if snr_db is not None:
+            std = (k / (2.0 * 10 ** (snr_db / 10.0))) ** 0.5
+            gd = torch.Generator(device=device).manual_seed(seed * 7919 + i)
+            u = torch.rand(n, generator=gd, device=device, dtype=torch.float64).clamp_min(1e-300)
+            v = torch.rand(n, generator=gd, device=device, dtype=torch.float64)
+            x = x + std * torch.sqrt(-2 * torch.log(u)) * torch.exp(2j * torch.pi * v)
+        out.append(x.contiguous())
+        del xf
+    return out
+
+
+def stage_bytes(info, stage, count):
+    """Algorithmic bytes of one stage per transform (DESIGN.md 'Measurement')."""
+    if stage == "gather":
+        return 16 * info["gather_samples"] + info["gather_tap_bytes"] + 16 * info["x_samp_size"]
+    if stage == "estimate":
+        # read the bucket spectra once, write (loc:4 B, val:16 B) per recovered coefficient
+        return 16 * info["x_samp_size"] + 20 * count
+    if stage == "bucket_fft":
+        return 2 * 16 * info["x_samp_size"]
+    if stage == "select":
+        return 16 * info["loops_loc"] * info["B_loc"]
+    return 0
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    rank, world, local = env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0)
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- this engine has no CPU path")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    import sfft_b200.sfft as sfft_mod
+    from sfft_b200 import _lib
+    L = _lib.load()
+
+    version, n, k, snr_db, desc = WORKLOADS[args.workload]
+    plan = sfft_mod.sfft(n, k, version, strict_parameters=False)
+    plan.set_stream(torch.cuda.current_stream().cuda_stream)
+    info = plan.info()
+
+    # rotate over several distinct signals; each is >= L2-sized at the default workload,
+    # smaller workloads additionally get an explicit L2 flush between steps
+    nsig_rot = max(2, min(4, (1 << 28) // n)) if n <= (1 << 26) else 1
+    signals = synth_signals(torch, n, k, nsig_rot, 1234 + rank, snr_db, dev)
+    flush = None
+    if n * 16 < 256 * 1024 * 1024:
+        flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    libc = C.CDLL(None)
+    libc.srand(17 + rank)
+    libc.srand48(12345 + rank)
+
+    def step(i):
+        plan.execute_device(signals[i % nsig_rot], None, sync=False)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        step(i)
+        if flush is not None:
+            flush.zero_()
+    barrier()
+
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.sfftb_launch_count()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+          for _ in range(args.steps)]
+    barrier()
+    t_wall0 = time.perf_counter()
+    for i in range(args.steps):
+        ev[i][0].record()
+        step(i)
+        ev[i][1].record()
+        if flush is not None:
+            flush.zero_()          # outside the per-step events
+    barrier()
+    t_wall = time.perf_counter() - t_wall0
+    launches = L.sfftb_launch_count() - launches0
+    ms_steps = [a.elapsed_time(b) for a, b in ev]
+    total_ms = sum(ms_steps)
+    clocks = sampler.stop() if rank == 0 else None
+    count = plan.execute_device(signals[0], None, sync=True)
+
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms_max = float(t.item())
+    value = world * args.steps * n / (total_ms_max * 1e-3) / 1e9
+
+    # ---- per-stage device times (separate pass, events between stages) ----
+    plan.stage_timing(True)
+    acc = {}
+    reps = max(3, min(10, args.steps))
+    for i in range(reps):
+        step(i)
+        for nm, ms in plan.stage_times().items():
+            acc.setdefault(nm, []).append(ms)
+        if flush is not None:
+            flush.zero_()
+    plan.stage_timing(False)
+    stages = {nm: sum(v) / len(v) for nm, v in acc.items()}
+
+    # ---- e2e through the legacy host API (rank-local, all ranks concurrently) ----
+    h_in = L.sfft_malloc(16 * n)
+    h_out = L.sfft_malloc(16 * n)
+    e2e_steps = max(1, min(args.steps, 10))
+    host_sig = signals[0].cpu().numpy()
+    C.memmove(h_in, host_sig.ctypes.data, 16 * n)
+    for _ in range(min(2, args.warmup)):
+        L.sfft_exec(plan.sfft_plan, h_in, h_out)
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        L.sfft_exec(plan.sfft_plan, h_in, h_out)
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+    e2e_value = world * e2e_steps * n / float(te.item()) / 1e9
+    L.sfft_free(h_in)
+    L.sfft_free(h_out)
+
+    if rank == 0:
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s"
+
+        def roof(stage):
+            ms = stages.get(stage)
+            if not ms:
+                return None
+            b = stage_bytes(info, stage, count)
+            ach = b / (ms * 1e-3) / 1e9
+            return {"kernel": stage, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                    "frac": ach / hbm_peak, "traffic": None, "ms": ms, "algorithmic_bytes": b,
+                    "peak_source": peak_src}
+
+        dominant = max(stages, key=stages.get) if stages else None
+        line = {
+            "metric": "sfft_exec throughput", "value": value, "unit": "Gsamples/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {desc}", "n": n, "k": k, "version": version,
+                       "signals_per_gpu_per_step": 1,
+                       "cache": ("input %d MiB > L2, %d signals rotated" % (16 * n >> 20, nsig_rot))
+                       + ("" if flush is None else ", 256 MiB L2 flush between steps"),
+                       "recovered_coefficients": int(count),
+                       "plan": {kk: info[kk] for kk in ("B_loc", "B_est", "loops_loc", "loops_est", "w_loc",
+                                                       "w_est", "W_Comb", "Comb_loops", "x_samp_size")}},
+            "e2e": {"value": e2e_value, "unit": "Gsamples/s", "h2d_bytes_per_step": 16 * n,
+                    "d2h_bytes_per_step": 16 * n, "steps": e2e_steps,
+                    "api": "sfft_exec(plan, host_in, host_out), pinned buffers from sfft_malloc"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": roof(dominant) if dominant else None,
+            "roofline_gather": roof("gather"),
+            "stage_ms": stages,
+            "wall_ms_per_step": 1e3 * t_wall / args.steps,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                line["cpu_baseline"] = cpu_reference_run(args.workload, 1, 1, 0, budget_s=90.0)
+            except Exception as e:     # the baseline leg must not sink the bench line
+                line["cpu_baseline"] = {"unavailable": repr(e)}
+        print(json.dumps(line))
+    plan.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference_arm(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,89 @@
+// common.cuh -- shared device/host helpers for the sm_100a sparse-FFT engine.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+namespace sfftb {
+
+typedef double2 cplx;   // (x = re, y = im), 16-byte aligned -> LDG.E.128 / STG.E.128
+
+// ---- error plumbing --------------------------------------------------------
+void set_error(const std::string &msg);
+extern long long g_launches;
+
+#define SFFTB_CUDA(call)                                                            \
+  do {                                                                              \
+    cudaError_t e__ = (call);                                                       \
+    if (e__ != cudaSuccess) {                                                       \
+      char buf__[512];                                                              \
+      snprintf(buf__, sizeof buf__, "%s:%d: %s -> %s", __FILE__, __LINE__, #call,   \
+               cudaGetErrorString(e__));                                            \
+      ::sfftb::set_error(buf__);                                                    \
+      return -1;                                                                    \
+    }                                                                               \
+  } while (0)
+
+#define SFFTB_LAUNCH_CHECK()                                                        \
+  do {                                                                              \
+    ::sfftb::g_launches++;                                                          \
+    cudaError_t e__ = cudaGetLastError();                                           \
+    if (e__ != cudaSuccess) {                                                       \
+      char buf__[512];                                                              \
+      snprintf(buf__, sizeof buf__, "%s:%d: kernel launch -> %s", __FILE__,         \
+               __LINE__, cudaGetErrorString(e__));                                  \
+      ::sfftb::set_error(buf__);                                                    \
+      return -1;                                                                    \
+    }                                                                               \
+  } while (0)
+
+// ---- exactly-rounded complex arithmetic ------------------------------------
+// The parity contract is "one IEEE rounding per product and per sum", the same
+// as the reference's SSE2 mul/hadd sequences (cf12.cc:243-256).  The intrinsics
+// below are never contracted into FMAs, whatever -fmad says.
+__device__ __forceinline__ cplx cmul_rn(cplx a, cplx b)
+{
+  const double p0 = __dmul_rn(a.x, b.x), p1 = __dmul_rn(a.y, b.y);
+  const double p2 = __dmul_rn(a.x, b.y), p3 = __dmul_rn(a.y, b.x);
+  return make_double2(__dsub_rn(p0, p1), __dadd_rn(p2, p3));
+}
+__device__ __forceinline__ cplx cadd_rn(cplx a, cplx b)
+{
+  return make_double2(__dadd_rn(a.x, b.x), __dadd_rn(a.y, b.y));
+}
+__device__ __forceinline__ cplx csub_rn(cplx a, cplx b)
+{
+  return make_double2(__dsub_rn(a.x, b.x), __dsub_rn(a.y, b.y));
+}
+__device__ __forceinline__ double cabs2_rn(cplx a)
+{
+  return __dadd_rn(__dmul_rn(a.x, a.x), __dmul_rn(a.y, a.y));
+}
+
+// read-only 16-byte load that does not pollute L1 (random gathers of the signal)
+__device__ __forceinline__ cplx ldg_stream(const cplx *p)
+{
+  cplx r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];"
+               : "=d"(r.x), "=d"(r.y)
+               : "l"(p));
+  return r;
+}
+
+__host__ __device__ __forceinline__ int ilog2(unsigned long long v)
+{
+  int l = 0;
+  while (v > 1) { v >>= 1; l++; }
+  return l;
+}
+
+__device__ __forceinline__ unsigned bitrev(unsigned v, int bits)
+{
+  return bits == 0 ? 0u : (__brev(v) >> (32 - bits));
+}
+
+inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+}  // namespace sfftb

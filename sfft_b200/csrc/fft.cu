@@ -1,0 +1,159 @@
+// fft.cu -- shared-memory tiled radix-2 DIT FFT passes (see fft.cuh).
+#include "fft.cuh"
+
+#include <math.h>
+
+namespace sfftb {
+
+// ---------------------------------------------------------------------------
+// host twiddles (octant rule; same definition the oracle pins in fft_ref.c)
+// ---------------------------------------------------------------------------
+void host_twiddle(long k, long n, double *re, double *im)
+{
+  const long n2 = n / 2, n4 = n / 4, n8 = n / 8;
+  const double unit = M_PI / (double)(n2 > 0 ? n2 : 1);   // 2*pi/n
+  double c, s;
+  if (k <= n8) {
+    const double a = (double)k * unit;
+    c = cos(a); s = sin(a);
+  } else if (k <= n4) {
+    const double a = (double)(n4 - k) * unit;
+    c = sin(a); s = cos(a);
+  } else if (k <= n4 + n8) {
+    const double a = (double)(k - n4) * unit;
+    c = -sin(a); s = cos(a);
+  } else {
+    const double a = (double)(n2 - k) * unit;
+    c = -cos(a); s = sin(a);
+  }
+  *re = c;
+  *im = -s;
+}
+
+void host_twiddle_table(long n, cplx *out)
+{
+  if (n < 2) { out[0] = make_double2(1.0, -0.0); return; }
+  for (long k = 0; k < n / 2; k++) host_twiddle(k, n, &out[k].x, &out[k].y);
+}
+
+// ---------------------------------------------------------------------------
+// one pass = stages [s0, s0+ns) of the DIT graph on a tile of 2^ns rows (stride
+// 2^s0 elements) by 2^logT adjacent columns, staged in shared memory
+// ---------------------------------------------------------------------------
+constexpr int kFftThreads = 256;
+constexpr int kMaxTileLog = 11;        // 2048 points = 32 KB of shared memory
+constexpr int kLaterPassStages = 8;    // keeps >= 8 adjacent columns (128 B) per row
+
+template <bool TABLE>
+__global__ void __launch_bounds__(kFftThreads)
+fft_pass_kernel(cplx *base, int s0, int ns, int logT, long long fft_stride,
+                long long sig_stride, const cplx *__restrict__ tw, int log_twN, int sign)
+{
+  extern __shared__ cplx tile[];
+  const int T = 1 << logT;
+  const int elems = 1 << (ns + logT);
+  const int lhi_bits = s0 - logT;
+  const unsigned tile_id = blockIdx.x;
+  const unsigned Lhi = tile_id & ((1u << lhi_bits) - 1u);
+  const unsigned long long H = (unsigned long long)(tile_id >> lhi_bits);
+  cplx *fft = base + (long long)blockIdx.z * sig_stride + (long long)blockIdx.y * fft_stride;
+  const unsigned long long base_idx =
+      (H << (s0 + ns)) | ((unsigned long long)Lhi << logT);
+
+  for (int e = threadIdx.x; e < elems; e += kFftThreads) {
+    const int r = e >> logT, c = e & (T - 1);
+    tile[e] = fft[base_idx + ((unsigned long long)r << s0) + c];
+  }
+  __syncthreads();
+
+  const unsigned long long Lfixed = (unsigned long long)Lhi << logT;
+  for (int st = 0; st < ns; st++) {
+    const int s = s0 + st;
+    for (int q = threadIdx.x; q < elems / 2; q += kFftThreads) {
+      const int c = q & (T - 1);
+      const int rr = q >> logT;
+      const int r_lo = rr & ((1 << st) - 1);
+      const int r_hi = rr >> st;
+      const int r0 = (r_hi << (st + 1)) | r_lo;
+      const int r1 = r0 | (1 << st);
+      const unsigned long long k = ((unsigned long long)r_lo << s0) | Lfixed | (unsigned)c;
+      cplx w;
+      if (TABLE) {
+        w = __ldg(&tw[k << (log_twN - s - 1)]);
+      } else {
+        double sn, cs;
+        sincospi((double)k / (double)(1ull << s), &sn, &cs);
+        w = make_double2(cs, -sn);
+      }
+      if (sign > 0) w.y = -w.y;
+      const int i0 = (r0 << logT) | c, i1 = (r1 << logT) | c;
+      const cplx u = tile[i0], v = tile[i1];
+      const cplx t = cmul_rn(w, v);
+      tile[i0] = cadd_rn(u, t);
+      tile[i1] = csub_rn(u, t);
+    }
+    __syncthreads();
+  }
+
+  for (int e = threadIdx.x; e < elems; e += kFftThreads) {
+    const int r = e >> logT, c = e & (T - 1);
+    fft[base_idx + ((unsigned long long)r << s0) + c] = tile[e];
+  }
+}
+
+int fft_dit_inplace(cplx *base, int logN, int nfft, long long fft_stride, int nsig,
+                    long long sig_stride, const cplx *tw, int log_twN, int sign,
+                    cudaStream_t st)
+{
+  if (logN <= 0 || nfft <= 0 || nsig <= 0) return 0;
+  if (tw && log_twN < logN) {
+    set_error("fft_dit_inplace: twiddle table smaller than the transform");
+    return -1;
+  }
+  int s0 = 0;
+  while (s0 < logN) {
+    int ns, logT;
+    if (s0 == 0) {
+      ns = logN < kMaxTileLog ? logN : kMaxTileLog;
+      logT = 0;
+    } else {
+      const int rem = logN - s0;
+      ns = rem < kLaterPassStages ? rem : kLaterPassStages;
+      logT = kMaxTileLog - ns;
+      if (logT > s0) logT = s0;
+    }
+    const long long tiles = 1ll << (logN - ns - logT);
+    dim3 grid((unsigned)tiles, (unsigned)nfft, (unsigned)nsig);
+    const size_t smem = sizeof(cplx) << (ns + logT);
+    if (tw)
+      fft_pass_kernel<true><<<grid, kFftThreads, smem, st>>>(base, s0, ns, logT, fft_stride,
+                                                            sig_stride, tw, log_twN, sign);
+    else
+      fft_pass_kernel<false><<<grid, kFftThreads, smem, st>>>(base, s0, ns, logT, fft_stride,
+                                                             sig_stride, tw, log_twN, sign);
+    SFFTB_LAUNCH_CHECK();
+    s0 += ns;
+  }
+  return 0;
+}
+
+__global__ void bitrev_permute_kernel(const cplx *__restrict__ in, cplx *__restrict__ out,
+                                      int logN)
+{
+  const long long n = 1ll << logN;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n;
+       i += (long long)gridDim.x * blockDim.x)
+    out[bitrev((unsigned)i, logN)] = in[i];
+}
+
+int bitrev_permute(const cplx *in, cplx *out, int logN, cudaStream_t st)
+{
+  const long long n = 1ll << logN;
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  bitrev_permute_kernel<<<blocks, 256, 0, st>>>(in, out, logN);
+  SFFTB_LAUNCH_CHECK();
+  return 0;
+}
+
+}  // namespace sfftb

@@ -1,0 +1,110 @@
+// plan.cuh -- internal plan object behind the public sfft_plan (include/sfft.h).
+//
+// Mirrors the reference's plan data (struct sfft_v1v2_data / sfft_v3_data,
+// src/sfft.h:78-154) but everything a transform touches lives in HBM, and mode
+// (v1 vs v2) is per-plan state instead of the reference's process globals
+// (src/common.cc:22-23).
+#pragma once
+
+#include <vector>
+
+#include "../../include/sfft.h"
+#include "common.cuh"
+#include "plan_builder.cuh"
+#include "v12_kernels.cuh"
+
+namespace sfftb {
+
+constexpr int kStageSlots = 8;     // ring of pinned staging buffers for per-transform draws
+constexpr int kMaxStages = 16;
+
+struct StageTimer {
+  bool enabled = false;
+  int count = 0;
+  const char *names[kMaxStages];
+  cudaEvent_t ev[kMaxStages + 1];
+  bool created = false;
+};
+
+struct PlanV12 {
+  // ---- derived parameters (src/sfft.cc:298-353) ----
+  int with_comb = 0;
+  int B_loc = 0, B_est = 0, B_thresh = 0, W_Comb = 0, Comb_loops = 0;
+  int loops_loc = 0, loops_thresh = 0, loops_est = 0;
+  int b_loc = 0, b_est = 0;
+  double tol_loc = 0, tol_est = 0, lobe_loc = 0, lobe_est = 0;
+  long long x_samp_size = 0;
+  LoopGeom geom;
+  DeviceFilter filt[2];            // [0] location, [1] estimation
+  cplx *d_tw = nullptr;            // twiddle table for the bucket FFTs
+  int log_twN = 0;
+
+  // ---- scratch, sized for `cap` signals ----
+  int cap = 0;
+  long long max_hits = 0, max_voted = 0;
+  cplx *d_xs = nullptr;            // [cap][x_samp_size]
+  int *d_J = nullptr;              // [cap][loops_loc][num]
+  unsigned *d_bitmap = nullptr;    // [cap][loops_loc][B_loc/32]
+  unsigned long long *d_gkeys = nullptr;
+  long long gkeys_per_sig = 0;
+  int *d_voted = nullptr;          // [cap][max_voted]
+  int *d_voted_count = nullptr;    // [cap]
+  int *d_hit_loc = nullptr;        // [cap][max_hits]
+  cplx *d_hit_val = nullptr;       // [cap][max_hits]
+  int *d_count = nullptr;          // [cap]   (v2: size of the pre-filled list)
+  // v2
+  cplx *d_comb_xs = nullptr;       // [cap][Comb_loops][W]
+  int *d_comb_J = nullptr;         // [cap][Comb_loops][num]
+  unsigned *d_comb_bm = nullptr;   // [cap][Comb_loops][W/32]
+  unsigned *d_appr_bm = nullptr;   // [cap][W/32]
+  int *d_approved = nullptr;       // [cap][W]
+  int *d_num_comb = nullptr;       // [cap]
+  // per-transform draws: a[loops], ai[loops] per signal, then comb offsets
+  int *d_stage = nullptr;          // [cap * ints_per_sig]
+  int ints_per_sig = 0;
+  int *h_stage[kStageSlots] = {nullptr};
+  cudaEvent_t stage_ev[kStageSlots];
+  int stage_next = 0;
+  long long *h_counts = nullptr;   // pinned
+};
+
+struct PlanV3;   // v3.cu
+
+struct PlanImpl {
+  int version = 1;     // 1, 2, 3
+  int n = 0, logn = 0, k = 0;
+  int device = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  PlanV12 v12;
+  PlanV3 *v3 = nullptr;
+  // legacy host-pointer path
+  cplx *d_in = nullptr;   long long d_in_elems = 0;
+  cplx *d_out = nullptr;
+  int last_nsig = 0;
+  StageTimer timer;
+};
+
+// plan_v12.cu
+int v12_derive(PlanImpl *p, int n, int k, int with_comb);
+int v12_build(PlanImpl *p);
+int v12_ensure_capacity(PlanImpl *p, int nsig);
+void v12_free(PlanImpl *p);
+int v12_draw(const PlanImpl *p, sfftb_draw *d);
+int v12_exec(PlanImpl *p, const cplx *d_in, long long stride, int nsig, const sfftb_draw *draws);
+
+// timing helpers
+void timer_begin(PlanImpl *p);
+void timer_mark(PlanImpl *p, const char *name);
+
+// v3.cu
+int v3_build(PlanImpl *p, int n, int k);
+void v3_free(PlanImpl *p);
+int v3_draw(const PlanImpl *p, sfftb_draw *d);
+int v3_exec(PlanImpl *p, const cplx *d_in, long long stride, int nsig, const sfftb_draw *draws);
+int v3_info(const PlanImpl *p, sfftb_info *info);
+int v3_result(PlanImpl *p, const int **loc, const cplx **val, const int **count, long long *cap);
+int v3_filter_sizes(const PlanImpl *p, int which, int *w, int *fw_len);
+DeviceFilter *v3_filter(PlanImpl *p, int which);
+long long v3_debug_fetch(PlanImpl *p, const char *what, void *dst, size_t capacity);
+
+}  // namespace sfftb

@@ -1,0 +1,397 @@
+// plan_v12.cu -- plan derivation and transform driver for sFFT v1 / v2.
+//
+// Host-side mirror of sfft_v1v2_make_plan (src/sfft.cc:298-392) and of outer_loop's
+// control flow (src/computefourier-1.0-2.0.cc:438-541); all data-path work is in
+// the kernels of v12_kernels.cu / fft.cu.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include "fft.cuh"
+#include "plan.cuh"
+
+namespace sfftb {
+
+namespace {
+
+struct ParamRow {
+  int by_k, with_comb, key;
+  double Bcst_loc, Bcst_est, Comb_cst;
+  int loc_loops, est_loops, threshold_loops, comb_loops;
+  double tolerance_loc, tolerance_est;
+};
+
+const ParamRow kParamRows[] = {
+#include "param_table.inc"
+};
+
+// src/utils.cc:243-248
+int floor_to_pow2(double x)
+{
+  unsigned int ans;
+  for (ans = 1; ans <= x; ans <<= 1) {}
+  return (int)(ans / 2);
+}
+
+// src/utils.cc:41-46
+int gcd_ref(int a, int b)
+{
+  while (a % b != 0) {
+    const int r = a % b;
+    a = b;
+    b = r;
+  }
+  return b;
+}
+
+// src/utils.cc:85-100
+int mod_inverse(int a, int n)
+{
+  int i = n, v = 0, d = 1;
+  while (a > 0) {
+    const int t = i / a, x = a;
+    a = i % x;
+    i = x;
+    const int nd = v - t * d;
+    v = d;
+    d = nd;
+  }
+  v %= n;
+  if (v < 0) v = (v + n) % n;
+  return v;
+}
+
+}  // namespace
+
+int mod_inverse_pub(int a, int n) { return mod_inverse(a, n); }
+int gcd_pub(int a, int b) { return gcd_ref(a, b); }
+
+int v12_derive(PlanImpl *p, int n_req, int k, int with_comb)
+{
+  PlanV12 &v = p->v12;
+  // defaults, src/sfft.cc:306-314
+  double Bcst_loc = 1, Bcst_est = 1, Comb_cst = 2;
+  int loc_loops = 4, est_loops = 16, threshold_loops = 3, comb_loops = 1;
+  double tol_loc = 1.e-8, tol_est = 1.e-8;
+  // src/sfft.cc:316-327: for k > 50 the by-K table is searched with n as the key
+  const int by_k = (unsigned)k > 50 ? 1 : 0;
+  for (const ParamRow &r : kParamRows) {
+    if (r.by_k == by_k && r.with_comb == with_comb && r.key == n_req) {
+      Bcst_loc = r.Bcst_loc; Bcst_est = r.Bcst_est; Comb_cst = r.Comb_cst;
+      loc_loops = r.loc_loops; est_loops = r.est_loops;
+      threshold_loops = r.threshold_loops; comb_loops = r.comb_loops;
+      tol_loc = r.tolerance_loc; tol_est = r.tolerance_est;
+      break;
+    }
+  }
+  const unsigned n = (unsigned)floor_to_pow2(n_req);
+  if ((int)n != n_req || n < 4) {
+    set_error("sfft_make_plan: n must be a power of two >= 4 (the reference's transform is "
+              "undefined otherwise: it plans for floor_to_pow2(n) but executes with n)");
+    return -1;
+  }
+  if (k < 1) { set_error("sfft_make_plan: k must be >= 1"); return -1; }
+
+  // src/sfft.cc:332-349
+  const double BB_loc = (unsigned)(Bcst_loc * sqrt((double)(int)n * (unsigned)k / (log2((double)n))));
+  const double BB_est = (unsigned)(Bcst_est * sqrt((double)(int)n * (unsigned)k / (log2((double)n))));
+  if (BB_loc < 1 || BB_est < 1) { set_error("sfft_make_plan: bucket count underflows"); return -1; }
+  v.with_comb = with_comb;
+  v.lobe_loc = 0.5 / BB_loc;
+  v.lobe_est = 0.5 / BB_est;
+  v.b_loc = (int)(1.2 * 1.1 * ((double)n / BB_loc));
+  v.b_est = (int)(1.4 * 1.1 * ((double)n / BB_est));
+  v.B_loc = floor_to_pow2(BB_loc);
+  v.B_thresh = 2 * k;
+  v.B_est = floor_to_pow2(BB_est);
+  v.W_Comb = floor_to_pow2(Comb_cst * n / v.B_loc);
+  v.Comb_loops = comb_loops;
+  v.loops_loc = loc_loops;
+  v.loops_thresh = threshold_loops;
+  v.loops_est = est_loops;
+  v.tol_loc = tol_loc;
+  v.tol_est = tol_est;
+  v.x_samp_size = (long long)v.loops_loc * v.B_loc + (long long)v.loops_est * v.B_est;
+
+  const int loops = v.loops_loc + v.loops_est;
+  if (loops > SFFTB_MAX_LOOPS || v.Comb_loops > SFFTB_MAX_COMB_LOOPS) {
+    set_error("sfft_make_plan: loop count exceeds SFFTB_MAX_LOOPS");
+    return -1;
+  }
+  if ((unsigned)v.B_loc > n || (unsigned)v.B_est > n) {
+    set_error("sfft_make_plan: more buckets than samples (reference asserts n % B == 0, cf12.cc:215)");
+    return -1;
+  }
+  // find_largest_indices asserts n >= num+1 (src/utils.cc:134) for every loop
+  // (cf12.cc:301) and for the Comb spectrum (cf12.cc:78)
+  if (v.B_loc < v.B_thresh + 1 || v.B_est < v.B_thresh + 1) {
+    set_error("sfft_make_plan: 2k+1 exceeds the bucket count (reference asserts, utils.cc:134)");
+    return -1;
+  }
+  if (with_comb && (v.W_Comb < v.B_thresh + 1 || (unsigned)v.W_Comb > n)) {
+    set_error("sfft_make_plan: 2k+1 exceeds W_Comb (reference asserts, utils.cc:134 via cf12.cc:78)");
+    return -1;
+  }
+
+  p->n = (int)n;
+  p->logn = ilog2(n);
+  p->k = k;
+  LoopGeom &g = v.geom;
+  g.n_mask = (int)n - 1;
+  g.logn = p->logn;
+  g.loops = loops;
+  g.loops_loc = v.loops_loc;
+  g.logB[0] = ilog2((unsigned)v.B_loc);
+  g.logB[1] = ilog2((unsigned)v.B_est);
+  g.x_samp_size = v.x_samp_size;
+  return 0;
+}
+
+int v12_build(PlanImpl *p)
+{
+  PlanV12 &v = p->v12;
+  cudaStream_t st = p->stream;
+  const int n = p->n;
+  // filters (src/sfft.cc:355-364): only n/B+1 response entries are ever read
+  // (cf12.cc:371-385), so keep the window [-n/2B, +n/2B]
+  const int half_loc = (n / v.B_loc) / 2, half_est = (n / v.B_est) / 2;
+  if (build_filter(p->logn, v.lobe_loc, v.tol_loc, v.b_loc, half_loc, &v.filt[0], st)) return -1;
+  if (build_filter(p->logn, v.lobe_est, v.tol_est, v.b_est, half_est, &v.filt[1], st)) return -1;
+  v.geom.w[0] = v.filt[0].w;
+  v.geom.w[1] = v.filt[1].w;
+
+  // twiddle table for the largest bucket FFT of this plan
+  int twN = v.B_loc > v.B_est ? v.B_loc : v.B_est;
+  if (v.with_comb && v.W_Comb > twN) twN = v.W_Comb;
+  v.log_twN = ilog2((unsigned)twN);
+  std::vector<cplx> tw((size_t)(twN / 2 > 0 ? twN / 2 : 1));
+  host_twiddle_table(twN, tw.data());
+  SFFTB_CUDA(cudaMalloc(&v.d_tw, sizeof(cplx) * tw.size()));
+  SFFTB_CUDA(cudaMemcpyAsync(v.d_tw, tw.data(), sizeof(cplx) * tw.size(), cudaMemcpyHostToDevice, st));
+  SFFTB_CUDA(cudaStreamSynchronize(st));
+
+  // result-list capacities
+  const long long seg = n / v.B_loc;
+  const int first_loops = v.loops_loc - v.loops_thresh + 1;
+  long long voted = first_loops > 0 ? (long long)first_loops * v.B_thresh * seg : 0;
+  if (voted > n) voted = n;
+  if (voted < 1) voted = 1;
+  v.max_voted = voted;
+  if (v.with_comb) {
+    long long nc = (long long)v.Comb_loops * v.B_thresh;
+    if (nc > v.W_Comb) nc = v.W_Comb;
+    v.max_hits = nc * (n / v.W_Comb);       // cf12.cc:505-512
+  } else {
+    v.max_hits = voted;
+  }
+  v.ints_per_sig = 2 * v.geom.loops + v.Comb_loops;
+  for (int i = 0; i < kStageSlots; i++) SFFTB_CUDA(cudaEventCreateWithFlags(&v.stage_ev[i], cudaEventDisableTiming));
+  return v12_ensure_capacity(p, 1);
+}
+
+static void v12_free_scratch(PlanV12 &v)
+{
+  cudaFree(v.d_xs); cudaFree(v.d_J); cudaFree(v.d_bitmap); cudaFree(v.d_gkeys);
+  cudaFree(v.d_voted); cudaFree(v.d_voted_count); cudaFree(v.d_hit_loc); cudaFree(v.d_hit_val);
+  cudaFree(v.d_count); cudaFree(v.d_comb_xs); cudaFree(v.d_comb_J); cudaFree(v.d_comb_bm);
+  cudaFree(v.d_appr_bm); cudaFree(v.d_approved); cudaFree(v.d_num_comb); cudaFree(v.d_stage);
+  for (int i = 0; i < kStageSlots; i++) {
+    if (v.h_stage[i]) cudaFreeHost(v.h_stage[i]);
+    v.h_stage[i] = nullptr;
+  }
+  if (v.h_counts) cudaFreeHost(v.h_counts);
+  v.h_counts = nullptr;
+  v.d_xs = nullptr; v.d_J = nullptr; v.d_bitmap = nullptr; v.d_gkeys = nullptr;
+  v.d_voted = nullptr; v.d_voted_count = nullptr; v.d_hit_loc = nullptr; v.d_hit_val = nullptr;
+  v.d_count = nullptr; v.d_comb_xs = nullptr; v.d_comb_J = nullptr; v.d_comb_bm = nullptr;
+  v.d_appr_bm = nullptr; v.d_approved = nullptr; v.d_num_comb = nullptr; v.d_stage = nullptr;
+  v.cap = 0;
+}
+
+int v12_ensure_capacity(PlanImpl *p, int nsig)
+{
+  PlanV12 &v = p->v12;
+  if (nsig <= v.cap) return 0;
+  SFFTB_CUDA(cudaStreamSynchronize(p->stream));
+  v12_free_scratch(v);
+  const long long S = nsig;
+  const int num = v.B_thresh;
+  const int words_loc = v.B_loc >= 32 ? v.B_loc / 32 : 1;
+  SFFTB_CUDA(cudaMalloc(&v.d_xs, sizeof(cplx) * S * v.x_samp_size));
+  SFFTB_CUDA(cudaMalloc(&v.d_J, sizeof(int) * S * v.loops_loc * num));
+  SFFTB_CUDA(cudaMalloc(&v.d_bitmap, sizeof(unsigned) * S * v.loops_loc * words_loc));
+  SFFTB_CUDA(cudaMalloc(&v.d_voted, sizeof(int) * S * v.max_voted));
+  SFFTB_CUDA(cudaMalloc(&v.d_voted_count, sizeof(int) * S));
+  SFFTB_CUDA(cudaMalloc(&v.d_hit_loc, sizeof(int) * S * v.max_hits));
+  SFFTB_CUDA(cudaMalloc(&v.d_hit_val, sizeof(cplx) * S * v.max_hits));
+  SFFTB_CUDA(cudaMalloc(&v.d_count, sizeof(int) * S));
+  SFFTB_CUDA(cudaMalloc(&v.d_stage, sizeof(int) * S * v.ints_per_sig));
+  long long gk = 0;
+  if (v.B_loc > 16384) gk = (long long)v.loops_loc * v.B_loc;
+  if (v.with_comb) {
+    const int W = v.W_Comb, words = W >= 32 ? W / 32 : 1;
+    SFFTB_CUDA(cudaMalloc(&v.d_comb_xs, sizeof(cplx) * S * v.Comb_loops * W));
+    SFFTB_CUDA(cudaMalloc(&v.d_comb_J, sizeof(int) * S * v.Comb_loops * num));
+    SFFTB_CUDA(cudaMalloc(&v.d_comb_bm, sizeof(unsigned) * S * v.Comb_loops * words));
+    SFFTB_CUDA(cudaMalloc(&v.d_appr_bm, sizeof(unsigned) * S * words));
+    SFFTB_CUDA(cudaMalloc(&v.d_approved, sizeof(int) * S * W));
+    SFFTB_CUDA(cudaMalloc(&v.d_num_comb, sizeof(int) * S));
+    if (W > 16384 && (long long)v.Comb_loops * W > gk) gk = (long long)v.Comb_loops * W;
+  }
+  v.gkeys_per_sig = gk;
+  if (gk) SFFTB_CUDA(cudaMalloc(&v.d_gkeys, sizeof(unsigned long long) * S * gk));
+  for (int i = 0; i < kStageSlots; i++)
+    SFFTB_CUDA(cudaHostAlloc(&v.h_stage[i], sizeof(int) * S * v.ints_per_sig, cudaHostAllocDefault));
+  SFFTB_CUDA(cudaHostAlloc(&v.h_counts, sizeof(long long) * S, cudaHostAllocDefault));
+  v.cap = nsig;
+  return 0;
+}
+
+void v12_free(PlanImpl *p)
+{
+  PlanV12 &v = p->v12;
+  v12_free_scratch(v);
+  free_filter(&v.filt[0]);
+  free_filter(&v.filt[1]);
+  cudaFree(v.d_tw);
+  v.d_tw = nullptr;
+  for (int i = 0; i < kStageSlots; i++) cudaEventDestroy(v.stage_ev[i]);
+}
+
+// One transform's worth of libc randomness, in the reference's order:
+// `loops` rejection loops of random() % n until odd (cf12.cc:465-474), then one
+// drand48() per Comb loop (cf12.cc:62).
+int v12_draw(const PlanImpl *p, sfftb_draw *d)
+{
+  const PlanV12 &v = p->v12;
+  const int n = p->n;
+  d->loops = v.geom.loops;
+  for (int i = 0; i < v.geom.loops; i++) {
+    int a = 0;
+    while (gcd_ref(a, n) != 1) a = (int)(random() % n);
+    d->a[i] = a;
+    d->ai[i] = mod_inverse(a, n);
+  }
+  if (v.with_comb) {
+    const int sigma = n / v.W_Comb;
+    for (int c = 0; c < v.Comb_loops; c++) d->comb_offset[c] = (int)(unsigned)floor(drand48() * sigma);
+  }
+  return 0;
+}
+
+int v12_exec(PlanImpl *p, const cplx *d_in, long long stride, int nsig, const sfftb_draw *draws)
+{
+  PlanV12 &v = p->v12;
+  cudaStream_t st = p->stream;
+  const LoopGeom &g = v.geom;
+  const int loops = g.loops, num = v.B_thresh;
+  if (v12_ensure_capacity(p, nsig)) return -1;
+  timer_begin(p);
+
+  // ---- stage the draws ----
+  const int slot = v.stage_next;
+  v.stage_next = (v.stage_next + 1) % kStageSlots;
+  SFFTB_CUDA(cudaEventSynchronize(v.stage_ev[slot]));
+  int *hs = v.h_stage[slot];
+  int *h_perm = hs;
+  int *h_coff = hs + (long long)nsig * 2 * loops;
+  for (int s = 0; s < nsig; s++) {
+    const sfftb_draw &d = draws[s];
+    memcpy(h_perm + (long long)s * 2 * loops, d.a, sizeof(int) * loops);
+    memcpy(h_perm + (long long)s * 2 * loops + loops, d.ai, sizeof(int) * loops);
+    for (int c = 0; c < v.Comb_loops; c++) h_coff[(long long)s * v.Comb_loops + c] = d.comb_offset[c];
+  }
+  SFFTB_CUDA(cudaMemcpyAsync(v.d_stage, hs, sizeof(int) * (long long)nsig * v.ints_per_sig,
+                             cudaMemcpyHostToDevice, st));
+  SFFTB_CUDA(cudaEventRecord(v.stage_ev[slot], st));
+  const int *d_perm = v.d_stage;
+  const int *d_coff = v.d_stage + (long long)nsig * 2 * loops;
+  SFFTB_CUDA(cudaMemsetAsync(v.d_voted_count, 0, sizeof(int) * nsig, st));
+  timer_mark(p, "stage_draws");
+
+  // ---- Comb pre-filter (v2)  cf12.cc:483-512 ----
+  if (v.with_comb) {
+    const int W = v.W_Comb, logW = ilog2((unsigned)W), words = W >= 32 ? W / 32 : 1;
+    if (launch_comb_sample(d_in, stride, d_coff, v.Comb_loops, logW, p->logn, v.d_comb_xs,
+                           (long long)v.Comb_loops * W, nsig, st)) return -1;
+    if (fft_dit_inplace(v.d_comb_xs, logW, v.Comb_loops, W, nsig, (long long)v.Comb_loops * W,
+                        v.d_tw, v.log_twN, -1, st)) return -1;
+    SelectArgs sa;
+    sa.xs = v.d_comb_xs; sa.xs_stride = (long long)v.Comb_loops * W; sa.row_stride = W;
+    sa.logB = logW; sa.num = num;
+    sa.J = v.d_comb_J; sa.J_sig_stride = (long long)v.Comb_loops * num;
+    sa.bitmap = v.d_comb_bm; sa.bm_sig_stride = (long long)v.Comb_loops * words;
+    sa.gkeys = W > 16384 ? v.d_gkeys : nullptr; sa.gk_sig_stride = v.gkeys_per_sig;
+    sa.row_begin = 0; sa.row_step = 1;
+    if (launch_select(sa, v.Comb_loops, nsig, st)) return -1;
+    if (launch_comb_merge(v.d_comb_bm, v.Comb_loops, W, p->n / W, v.d_appr_bm, v.d_approved,
+                          v.d_num_comb, v.d_count, nsig, st)) return -1;
+    timer_mark(p, "comb");
+  }
+
+  // ---- permuted windowed gather  cf12.cc:222-261 ----
+  GatherArgs ga;
+  ga.x = d_in; ga.x_stride = stride;
+  ga.taps[0] = v.filt[0].time; ga.taps[1] = v.filt[1].time;
+  ga.perm = d_perm; ga.xs = v.d_xs;
+  ga.loop_begin = 0; ga.loop_step = 1;
+  if (launch_gather(g, ga, loops, nsig, st)) return -1;
+  timer_mark(p, "gather");
+
+  // ---- bucket FFTs  cf12.cc:270-275 ----
+  if (v.B_loc == v.B_est) {
+    if (fft_dit_inplace(v.d_xs, g.logB[0], loops, v.B_loc, nsig, v.x_samp_size, v.d_tw, v.log_twN,
+                        -1, st)) return -1;
+  } else {
+    if (fft_dit_inplace(v.d_xs, g.logB[0], v.loops_loc, v.B_loc, nsig, v.x_samp_size, v.d_tw,
+                        v.log_twN, -1, st)) return -1;
+    if (fft_dit_inplace(v.d_xs + (long long)v.loops_loc * v.B_loc, g.logB[1], v.loops_est, v.B_est,
+                        nsig, v.x_samp_size, v.d_tw, v.log_twN, -1, st)) return -1;
+  }
+  timer_mark(p, "bucket_fft");
+
+  // ---- |.|^2 + top-2k per location loop  cf12.cc:278-302 ----
+  const int words_loc = v.B_loc >= 32 ? v.B_loc / 32 : 1;
+  SelectArgs sa;
+  sa.xs = v.d_xs; sa.xs_stride = v.x_samp_size; sa.row_stride = v.B_loc;
+  sa.logB = g.logB[0]; sa.num = num;
+  sa.J = v.d_J; sa.J_sig_stride = (long long)v.loops_loc * num;
+  sa.bitmap = v.d_bitmap; sa.bm_sig_stride = (long long)v.loops_loc * words_loc;
+  sa.gkeys = v.B_loc > 16384 ? v.d_gkeys : nullptr; sa.gk_sig_stride = v.gkeys_per_sig;
+  sa.row_begin = 0; sa.row_step = 1;
+  if (launch_select(sa, v.loops_loc, nsig, st)) return -1;
+  timer_mark(p, "select");
+
+  // ---- reverse-hash voting  cf12.cc:304-323 ----
+  VoteArgs va;
+  va.perm = d_perm;
+  va.J = v.d_J; va.J_sig_stride = sa.J_sig_stride;
+  va.bitmap = v.d_bitmap; va.bm_sig_stride = sa.bm_sig_stride;
+  va.comb_bitmap = v.with_comb ? v.d_appr_bm : nullptr;
+  va.comb_sig_stride = v.with_comb ? (v.W_Comb >= 32 ? v.W_Comb / 32 : 1) : 0;
+  va.W_mask = v.W_Comb - 1;
+  va.hits = v.d_voted; va.hits_cap = v.max_voted; va.count = v.d_voted_count;
+  va.num = num; va.thresh = v.loops_thresh;
+  if (launch_vote(g, va, nsig, st)) return -1;
+  timer_mark(p, "vote");
+
+  // ---- estimation  cf12.cc:341-419 ----
+  EstimateArgs ea;
+  ea.perm = d_perm;
+  ea.xs = v.d_xs; ea.xs_stride = v.x_samp_size;
+  ea.fwin[0] = v.filt[0].fwin; ea.fwin[1] = v.filt[1].fwin;
+  ea.fw_half[0] = v.filt[0].fw_half; ea.fw_half[1] = v.filt[1].fw_half;
+  ea.hits = v.d_voted; ea.hits_cap = v.max_voted;
+  ea.count = v.d_voted_count;
+  ea.approved = v.with_comb ? v.d_approved : nullptr;
+  ea.approved_stride = v.W_Comb;
+  ea.num_comb = v.d_num_comb;
+  ea.W = v.W_Comb; ea.n_over_W = v.with_comb ? p->n / v.W_Comb : 0;
+  ea.out_loc = v.d_hit_loc; ea.out_val = v.d_hit_val; ea.out_cap = v.max_hits;
+  if (launch_estimate(g, ea, nsig, v.max_hits, st)) return -1;
+  timer_mark(p, "estimate");
+  p->last_nsig = nsig;
+  return 0;
+}
+
+}  // namespace sfftb

@@ -1,0 +1,87 @@
+// v12_kernels.cuh -- device stages of the sFFT v1/v2 transform.
+//
+// Reference path (single-threaded CPU): outer_loop, src/computefourier-1.0-2.0.cc:438-541.
+// Here every stage is a grid over (bucket | candidate | hit) x loop x signal, so the
+// same kernels serve sfft_exec (one signal) and sfft_exec_many (a batch).
+#pragma once
+
+#include "common.cuh"
+
+namespace sfftb {
+
+constexpr int kMaxLoops = 64;   // == SFFTB_MAX_LOOPS in include/sfft.h
+
+// Layout of the per-signal bucket array x_samp (reference cf12.cc:228-230):
+//   loops_loc rows of B_loc, then loops_est rows of B_est.
+struct LoopGeom {
+  int n_mask;          // n - 1
+  int logn;
+  int loops, loops_loc;
+  int logB[2];         // [0] location loops, [1] estimation loops
+  int w[2];            // taps per filter
+  long long x_samp_size;
+};
+
+// permutation table per signal: a[0..loops) then ai[0..loops)  (cf12.cc:465-474)
+__host__ __device__ __forceinline__ long long perm_stride(int loops) { return 2ll * loops; }
+
+struct GatherArgs {
+  const cplx *x;            // signals
+  long long x_stride;       // elements between signals
+  const cplx *taps[2];
+  const int *perm;
+  cplx *xs;                 // [S][x_samp_size], written in bit-reversed bucket order
+  int loop_begin, loop_step;   // loops handled: loop_begin + blockIdx.y*loop_step (sharding)
+};
+
+struct SelectArgs {
+  const cplx *xs;  long long xs_stride;   // bucket spectra (natural order)
+  long long row_stride;                   // elements between consecutive rows
+  int logB, num;
+  int *J;          long long J_sig_stride;      // [S][rows][num]
+  unsigned *bitmap; long long bm_sig_stride;    // [S][rows][max(1,B/32)]
+  unsigned long long *gkeys; long long gk_sig_stride;   // global key scratch when B > 16384
+  int row_begin, row_step;
+};
+
+struct VoteArgs {
+  const int *perm;
+  const int *J;         long long J_sig_stride;
+  const unsigned *bitmap; long long bm_sig_stride;
+  const unsigned *comb_bitmap; long long comb_sig_stride; int W_mask;   // v2 only (else null)
+  int *hits;            long long hits_cap;
+  int *count;
+  int num, thresh;
+};
+
+struct EstimateArgs {
+  const int *perm;
+  const cplx *xs;       long long xs_stride;
+  const cplx *fwin[2];  int fw_half[2];
+  // v1: explicit hit list;  v2: implicit prefill list (jj*W + approved[i])
+  const int *hits;      long long hits_cap;
+  const int *count;
+  const int *approved;  long long approved_stride; const int *num_comb; int W, n_over_W;
+  int *out_loc;         cplx *out_val;  long long out_cap;
+};
+
+int launch_gather(const LoopGeom &g, const GatherArgs &a, int nloops, int nsig, cudaStream_t st);
+int launch_select(const SelectArgs &a, int nrows, int nsig, cudaStream_t st);
+int launch_vote(const LoopGeom &g, const VoteArgs &a, int nsig, cudaStream_t st);
+int launch_estimate(const LoopGeom &g, const EstimateArgs &a, int nsig, long long max_per_sig,
+                    cudaStream_t st);
+
+// v2: xs[c][bitrev(i)] = x[offset_c + i*sigma]   (cf12.cc:61-67)
+int launch_comb_sample(const cplx *x, long long x_stride, const int *comb_off, int comb_loops,
+                       int logW, int logn, cplx *cxs, long long cxs_stride, int nsig,
+                       cudaStream_t st);
+// v2: union of the per-loop selections -> sorted residue list, its size, and the
+// size of the pre-filled hit list (cf12.cc:492-512)
+int launch_comb_merge(const unsigned *loop_bitmaps, int comb_loops, int W, int n_over_W,
+                      unsigned *approved_bitmap, int *approved, int *num_comb, int *count,
+                      int nsig, cudaStream_t st);
+
+// legacy dense output: out[loc] = val (after a memset)   (sfft.cc:121-123, cf12.cc:413)
+int launch_scatter(const int *loc, const cplx *val, const int *count, cplx *out, cudaStream_t st);
+
+}  // namespace sfftb

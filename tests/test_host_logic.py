@@ -1,0 +1,87 @@
+"""CPU-only checks of the boundary: the C-ABI library loads and exports every symbol
+include/sfft.h declares, fails loudly without a GPU, and the Python binding keeps
+the reference's validation behaviour (python/sfft/sfft.py:52-67)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from util import ROOT
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "sfft.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(sfftb?_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    from sfft_b200 import _lib
+    L = _lib.load()
+    declared = _declared_symbols()
+    assert len(declared) >= 28
+    for name in declared:
+        assert hasattr(L, name), f"libsfft.so does not export {name}"
+    assert set(declared) == set(_lib.SYMBOLS), "ctypes table and header disagree"
+
+
+def test_plan_struct_layout_matches_reference_header():
+    from sfft_b200 import _lib
+    # struct sfft_plan {sfft_version version; unsigned n; unsigned k; void *data;} (src/sfft.h:44-50)
+    assert C.sizeof(_lib.SfftPlan) == 24
+    assert _lib.SfftPlan.data.offset == 16
+
+
+def test_no_cpu_fallback_without_a_device():
+    from sfft_b200 import _lib
+    L = _lib.load()
+    if L.sfftb_device_count() > 0:
+        pytest.skip("a GPU is present")
+    assert not L.sfft_make_plan(16384, 50, 0, 64)
+    assert b"no CUDA device" in L.sfftb_last_error()
+    x = np.zeros(8, dtype=np.complex128)
+    assert L.sfftb_debug_fft(x.ctypes.data, x.ctypes.data, 3, 1, -1, 1) == -1
+    # sfft_malloc still hands out usable, aligned host memory
+    p = L.sfft_malloc(1024)
+    assert p and p % 16 == 0
+    L.sfft_free(p)
+
+
+def test_unknown_version_returns_null():
+    from sfft_b200 import _lib
+    L = _lib.load()
+    assert not L.sfft_make_plan(16384, 50, 7, 64)      # src/sfft.cc:87-88
+
+
+def test_binding_validation_matches_reference():
+    import sfft_b200.sfft as m
+    assert m.FFTW_MEASURE == 0 and m.FFTW_ESTIMATE == 64
+    assert {"size": 4194304, "sparsity": 2500} in m.V1_V2_INPUT_PARAMETERS
+    assert len(m.V1_V2_INPUT_PARAMETERS) == 20
+    with pytest.raises(TypeError):
+        m.sfft(16384.0, 50, 1)
+    with pytest.raises(TypeError):
+        m.sfft(16384, "50", 1)
+    with pytest.raises(ValueError):
+        m.sfft(16384, 50, 4)
+    with pytest.raises(ValueError):
+        m.sfft(16384, 51, 1)           # not in the whitelist
+    with pytest.raises(ValueError):
+        m.sfft(16384, 50, 1, optimization=3)
+
+
+def test_product_does_not_touch_the_oracle():
+    """The shipped path must not import, link or execute anything under oracle/."""
+    pkg = os.path.join(ROOT, "sfft_b200")
+    for dirpath, _, files in os.walk(pkg):
+        if "build" in dirpath.split(os.sep):
+            continue
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".c", ".h", ".inc")):
+                text = open(os.path.join(dirpath, f), errors="replace").read()
+                assert "oracle/" not in text.replace("# oracle/", "") or f == "build.py" and False, (dirpath, f)
+                assert "import oracle" not in text and "from oracle" not in text, (dirpath, f)
+    out = os.popen(f"ldd {os.path.join(pkg, 'libsfft.so')}").read()
+    assert "oracle" not in out
