@@ -256,7 +256,11 @@ def run_ours(args):
 
     version, n, k, snr_db, desc = WORKLOADS[args.workload]
     plan = sfft_mod.sfft(n, k, version, strict_parameters=False)
-    plan.set_stream(torch.cuda.current_stream().cuda_stream)
+    # every kernel of the engine and every timing event go to ONE explicit stream
+    # (torch's default stream has handle 0, which the C ABI reads as "plan's own stream")
+    stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(stream)
+    plan.set_stream(stream.cuda_stream)
     info = plan.info()
 
     # rotate over several distinct signals; each is >= L2-sized at the default workload,

@@ -327,6 +327,38 @@ __device__ __forceinline__ double select_rank(const double *v, int cnt, int want
   return v[0];
 }
 
+// median_select networks (generated): MedianNet<L>::run(v) = v[(L-1)/2] of sorted v
+#include "median_networks.inc"
+
+// one (hit, loop) term: bucket / filter response, as the reference executes it
+__device__ __forceinline__ void estimate_term(const LoopGeom &g, const EstimateArgs &a,
+                                              const cplx *__restrict__ xs, unsigned ai, unsigned loc,
+                                              int j, double &out_re, double &out_im)
+{
+  const bool est = j >= g.loops_loc;
+  const int logB = est ? g.logB[1] : g.logB[0];
+  const int logseg = g.logn - logB;
+  const int seg = 1 << logseg;
+  const unsigned pos = (unsigned)(((unsigned long long)ai * loc) & (unsigned)g.n_mask);   // cf12.cc:370
+  unsigned bucket = pos >> logseg;
+  int dist = (int)(pos & (unsigned)(seg - 1));
+  if (dist > seg / 2) {                                                                   // :373-377
+    bucket = (bucket + 1) & ((1u << logB) - 1u);
+    dist -= seg;
+  }
+  const cplx sv = xs[loop_offset(g, j) + bucket];
+  const cplx *__restrict__ fw = est ? a.fwin[1] : a.fwin[0];
+  const cplx f = __ldg(&fw[(est ? a.fw_half[1] : a.fw_half[0]) - dist]);   // freq[(n - dist) % n], :378
+  const double ac = __dmul_rn(sv.x, f.x), bd = __dmul_rn(sv.y, f.y);
+  const double ad = __dmul_rn(sv.x, f.y), bc = __dmul_rn(sv.y, f.x);
+  const double den = __dadd_rn(__dmul_rn(f.x, f.x), __dmul_rn(f.y, f.y));
+  out_re = __ddiv_rn(__dadd_rn(ac, bd), den);
+  out_im = __ddiv_rn(__dsub_rn(ad, bc), den);              // :390-392: (a*d) + (-(b*c))
+}
+
+// L > 0: loop count known at compile time, everything in registers.
+// L == 0: generic fallback (loop count at run time, values in local memory).
+template <int L>
 __global__ void __launch_bounds__(128)
 estimate_kernel(LoopGeom g, EstimateArgs a, long long max_per_sig)
 {
@@ -340,9 +372,9 @@ estimate_kernel(LoopGeom g, EstimateArgs a, long long max_per_sig)
     total = a.count[s];
   }
   if (total > max_per_sig) total = max_per_sig;
-  const unsigned mask = (unsigned)g.n_mask;
-  const int mid = (g.loops - 1) / 2;     // cf12.cc:406
-  const int *perm = a.perm + (long long)s * perm_stride(g.loops) + g.loops;   // ai[]
+  const int loops = L > 0 ? L : g.loops;
+  const int mid = (loops - 1) / 2;     // cf12.cc:406
+  const int *__restrict__ perm = a.perm + (long long)s * perm_stride(g.loops) + g.loops;   // ai[]
   const cplx *__restrict__ xs = a.xs + (long long)s * a.xs_stride;
 
   for (long long h = blockIdx.x * (long long)blockDim.x + threadIdx.x; h < total;
@@ -351,37 +383,35 @@ estimate_kernel(LoopGeom g, EstimateArgs a, long long max_per_sig)
     if (a.approved) {
       const long long jj = h / nc;
       const int i = (int)(h - jj * nc);
-      loc = (unsigned)(jj * a.W + a.approved[(long long)s * a.approved_stride + i]);   // cf12.cc:508-511
+      loc = (unsigned)(jj * a.W + __ldg(&a.approved[(long long)s * a.approved_stride + i]));   // cf12.cc:508-511
     } else {
       loc = (unsigned)a.hits[(long long)s * a.hits_cap + h];
     }
-    double vr[kMaxLoops], vi[kMaxLoops];
-    for (int j = 0; j < g.loops; j++) {
-      const bool est = j >= g.loops_loc;
-      const int logB = est ? g.logB[1] : g.logB[0];
-      const int logseg = g.logn - logB;
-      const int seg = 1 << logseg;
-      const unsigned pos = (unsigned)(((unsigned long long)(unsigned)perm[j] * loc) & mask);
-      unsigned bucket = pos >> logseg;
-      int dist = (int)(pos & (unsigned)(seg - 1));
-      if (dist > seg / 2) {
-        bucket = (bucket + 1) & ((1u << logB) - 1u);
-        dist -= seg;
-      }
-      const cplx sv = xs[loop_offset(g, j) + bucket];
-      const cplx *__restrict__ fw = est ? a.fwin[1] : a.fwin[0];
-      const cplx f = __ldg(&fw[(est ? a.fw_half[1] : a.fw_half[0]) - dist]);   // freq[(n - dist) % n]
-      const double ac = __dmul_rn(sv.x, f.x), bd = __dmul_rn(sv.y, f.y);
-      const double ad = __dmul_rn(sv.x, f.y), bc = __dmul_rn(sv.y, f.x);
-      const double den = __dadd_rn(__dmul_rn(f.x, f.x), __dmul_rn(f.y, f.y));
-      vr[j] = __ddiv_rn(__dadd_rn(ac, bd), den);
-      vi[j] = __ddiv_rn(__dsub_rn(ad, bc), den);
+    double re, im;
+    if (L > 0) {
+      double vr[L > 0 ? L : 2], vi[L > 0 ? L : 2];
+#pragma unroll
+      for (int j = 0; j < (L > 0 ? L : 2); j++)
+        estimate_term(g, a, xs, (unsigned)__ldg(&perm[j]), loc, j, vr[j], vi[j]);
+      re = MedianNet<(L > 0 ? L : 2)>::run(vr);
+      im = MedianNet<(L > 0 ? L : 2)>::run(vi);
+    } else {
+      double vr[kMaxLoops], vi[kMaxLoops];
+      for (int j = 0; j < loops; j++)
+        estimate_term(g, a, xs, (unsigned)perm[j], loc, j, vr[j], vi[j]);
+      re = select_rank(vr, loops, mid);
+      im = select_rank(vi, loops, mid);
     }
-    const double re = select_rank(vr, g.loops, mid);
-    const double im = select_rank(vi, g.loops, mid);
     a.out_loc[(long long)s * a.out_cap + h] = (int)loc;
     a.out_val[(long long)s * a.out_cap + h] = make_double2(re, im);
   }
+}
+
+template <int L>
+static void launch_estimate_t(const LoopGeom &g, const EstimateArgs &a, dim3 grid, long long max_per_sig,
+                              cudaStream_t st)
+{
+  estimate_kernel<L><<<grid, 128, 0, st>>>(g, a, max_per_sig);
 }
 
 int launch_estimate(const LoopGeom &g, const EstimateArgs &a, int nsig, long long max_per_sig,
@@ -392,7 +422,18 @@ int launch_estimate(const LoopGeom &g, const EstimateArgs &a, int nsig, long lon
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   dim3 grid((unsigned)blocks, (unsigned)nsig);
-  estimate_kernel<<<grid, 128, 0, st>>>(g, a, max_per_sig);
+  switch (g.loops) {
+#define SFFTB_EST_CASE(N) case N: launch_estimate_t<N>(g, a, grid, max_per_sig, st); break;
+    // every total loop count of the reference's tables (parameters.cc) and defaults
+    SFFTB_EST_CASE(2) SFFTB_EST_CASE(3) SFFTB_EST_CASE(4) SFFTB_EST_CASE(5) SFFTB_EST_CASE(6)
+    SFFTB_EST_CASE(7) SFFTB_EST_CASE(8) SFFTB_EST_CASE(9) SFFTB_EST_CASE(10)
+    SFFTB_EST_CASE(11) SFFTB_EST_CASE(12) SFFTB_EST_CASE(13) SFFTB_EST_CASE(14)
+    SFFTB_EST_CASE(15) SFFTB_EST_CASE(16) SFFTB_EST_CASE(17) SFFTB_EST_CASE(18)
+    SFFTB_EST_CASE(19) SFFTB_EST_CASE(20) SFFTB_EST_CASE(21) SFFTB_EST_CASE(22)
+    SFFTB_EST_CASE(23) SFFTB_EST_CASE(24)
+#undef SFFTB_EST_CASE
+    default: launch_estimate_t<0>(g, a, grid, max_per_sig, st); break;
+  }
   SFFTB_LAUNCH_CHECK();
   return 0;
 }
