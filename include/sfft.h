@@ -197,6 +197,9 @@ int sfftb_debug_fft(const sfft_complex *in, sfft_complex *out, int log2n, int ba
                     int table_twiddles);
 int sfftb_debug_select(const double *mags, int B, int num, int batch, int *out_J);
 int sfftb_debug_dft_any(const sfft_complex *in, sfft_complex *out, int n);
+/* number of (a,b) pairs, out of `count` pseudo-random ones, for which the engine's
+ * reciprocal-based exact division differs from IEEE division (must be 0) */
+long long sfftb_debug_div_check(unsigned long long seed, long long count);
 
 /* per-stage device timings (ms) of the last transform when timing was enabled */
 int sfftb_enable_stage_timing(sfft_plan *plan, int on);

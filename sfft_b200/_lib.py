@@ -80,6 +80,7 @@ SYMBOLS = {
     "sfftb_debug_fft": (_ci, [_vp, _vp, _ci, _ci, _ci, _ci]),
     "sfftb_debug_select": (_ci, [_vp, _ci, _ci, _ci, _vp]),
     "sfftb_debug_dft_any": (_ci, [_vp, _vp, _ci]),
+    "sfftb_debug_div_check": (_ll, [C.c_ulonglong, _ll]),
     "sfftb_enable_stage_timing": (_ci, [_PP, _ci]),
     "sfftb_stage_times": (_ci, [_PP, _vp, _vp, _ci]),
     "sfftb_launch_count": (_ll, []),

@@ -408,8 +408,11 @@ int sfftb_set_filter(sfft_plan *plan, int which, const sfft_complex *time, const
   if (bind_device(p)) return -1;
   SFFTB_CUDA(cudaStreamSynchronize(p->stream));
   if (time) SFFTB_CUDA(cudaMemcpy(f->time, time, sizeof(cplx) * f->w, cudaMemcpyHostToDevice));
-  if (freq_window)
+  if (freq_window) {
     SFFTB_CUDA(cudaMemcpy(f->fwin, freq_window, sizeof(cplx) * (2ll * f->fw_half + 1), cudaMemcpyHostToDevice));
+    if (filter_refresh(f, p->stream)) return -1;
+    SFFTB_CUDA(cudaStreamSynchronize(p->stream));
+  }
   return 0;
 }
 
@@ -431,7 +434,7 @@ long long sfftb_debug_fetch(sfft_plan *plan, const char *what, void *dst, size_t
   else if (w == "bitmap") { src = v.d_bitmap; bytes = sizeof(unsigned) * (long long)v.loops_loc * (v.B_loc >= 32 ? v.B_loc / 32 : 1); }
   else if (w == "perm_a") { src = v.d_stage; bytes = sizeof(int) * loops; }
   else if (w == "perm_ai") { src = v.d_stage + loops; bytes = sizeof(int) * loops; }
-  else if (w == "twiddle") { src = v.d_tw; bytes = sizeof(cplx) * ((1ll << v.log_twN) / 2 > 0 ? (1ll << v.log_twN) / 2 : 1); }
+  else if (w == "twiddle") { src = v.d_tw; bytes = sizeof(cplx) * ((1ll << v.log_twN) > 1 ? (1ll << v.log_twN) - 1 : 1); }
   else if (w == "voted" || w == "hits" || w == "vals" || w == "comb_approved") {
     int c = 0;
     const int *cp = (w == "voted") ? v.d_voted_count
@@ -472,8 +475,8 @@ int sfftb_debug_fft(const sfft_complex *in, sfft_complex *out, int log2n, int ba
   for (int b = 0; b < batch; b++)
     if (bitrev_permute(d_a + b * n, d_b + b * n, log2n, 0)) return -1;
   if (table_twiddles) {
-    std::vector<cplx> tw((size_t)(n / 2 > 0 ? n / 2 : 1));
-    host_twiddle_table(n, tw.data());
+    std::vector<cplx> tw((size_t)(n > 1 ? n - 1 : 1));
+    host_twiddle_levels(n, tw.data());
     SFFTB_CUDA(cudaMalloc(&d_tw, sizeof(cplx) * tw.size()));
     SFFTB_CUDA(cudaMemcpy(d_tw, tw.data(), sizeof(cplx) * tw.size(), cudaMemcpyHostToDevice));
   }
@@ -524,6 +527,12 @@ int sfftb_debug_dft_any(const sfft_complex *in, sfft_complex *out, int n)
   SFFTB_CUDA(cudaMemcpy(out, d_y, sizeof(cplx) * n, cudaMemcpyDeviceToHost));
   cudaFree(d_x); cudaFree(d_y);
   return 0;
+}
+
+long long sfftb_debug_div_check(unsigned long long seed, long long count)
+{
+  if (sfftb_device_count() <= 0) { set_error("sfftb_debug_div_check: no CUDA device"); return -1; }
+  return run_div_check(seed, count);
 }
 
 int sfftb_enable_stage_timing(sfft_plan *plan, int on)

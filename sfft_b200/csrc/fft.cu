@@ -36,6 +36,15 @@ void host_twiddle_table(long n, cplx *out)
   for (long k = 0; k < n / 2; k++) host_twiddle(k, n, &out[k].x, &out[k].y);
 }
 
+void host_twiddle_levels(long n, cplx *out)
+{
+  // level s (0-based, half-size h = 2^s) holds W_{2h}^k, k < h, at offset h - 1.
+  // W_{2h}^k = e^{-2 pi i k / 2h} evaluated by the octant rule at size n: the same
+  // double whatever n >= 2h is (the scale factor is a power of two).
+  for (long h = 1; h < n; h <<= 1)
+    for (long k = 0; k < h; k++) host_twiddle(k * (n / (2 * h)), n, &out[h - 1 + k].x, &out[h - 1 + k].y);
+}
+
 // ---------------------------------------------------------------------------
 // one pass = stages [s0, s0+ns) of the DIT graph on a tile of 2^ns rows (stride
 // 2^s0 elements) by 2^logT adjacent columns, staged in shared memory
@@ -44,12 +53,16 @@ constexpr int kFftThreads = 256;
 constexpr int kMaxTileLog = 11;        // 2048 points = 32 KB of shared memory
 constexpr int kLaterPassStages = 8;    // keeps >= 8 adjacent columns (128 B) per row
 
+// TABLE: `tw` is the level-ordered twiddle table (host_twiddle_levels).  The first
+// pass (s0 == 0) copies levels [0, ns) next to the tile in shared memory; later
+// passes read their (column-contiguous) twiddles through L1/L2.
 template <bool TABLE>
 __global__ void __launch_bounds__(kFftThreads)
 fft_pass_kernel(cplx *base, int s0, int ns, int logT, long long fft_stride,
                 long long sig_stride, const cplx *__restrict__ tw, int log_twN, int sign)
 {
   extern __shared__ cplx tile[];
+  cplx *stw = tile + (1 << (ns + logT));      // only used when TABLE && s0 == 0
   const int T = 1 << logT;
   const int elems = 1 << (ns + logT);
   const int lhi_bits = s0 - logT;
@@ -64,6 +77,8 @@ fft_pass_kernel(cplx *base, int s0, int ns, int logT, long long fft_stride,
     const int r = e >> logT, c = e & (T - 1);
     tile[e] = fft[base_idx + ((unsigned long long)r << s0) + c];
   }
+  if (TABLE && s0 == 0)
+    for (int e = threadIdx.x; e < (1 << ns) - 1; e += kFftThreads) stw[e] = __ldg(&tw[e]);
   __syncthreads();
 
   const unsigned long long Lfixed = (unsigned long long)Lhi << logT;
@@ -79,7 +94,7 @@ fft_pass_kernel(cplx *base, int s0, int ns, int logT, long long fft_stride,
       const unsigned long long k = ((unsigned long long)r_lo << s0) | Lfixed | (unsigned)c;
       cplx w;
       if (TABLE) {
-        w = __ldg(&tw[k << (log_twN - s - 1)]);
+        w = s0 == 0 ? stw[(1 << s) - 1 + (int)k] : __ldg(&tw[(1ull << s) - 1ull + k]);
       } else {
         double sn, cs;
         sincospi((double)k / (double)(1ull << s), &sn, &cs);
@@ -124,7 +139,14 @@ int fft_dit_inplace(cplx *base, int logN, int nfft, long long fft_stride, int ns
     }
     const long long tiles = 1ll << (logN - ns - logT);
     dim3 grid((unsigned)tiles, (unsigned)nfft, (unsigned)nsig);
-    const size_t smem = sizeof(cplx) << (ns + logT);
+    size_t smem = sizeof(cplx) << (ns + logT);
+    if (tw && s0 == 0) smem += sizeof(cplx) << ns;
+    static bool attr_set = false;
+    if (!attr_set) {
+      SFFTB_CUDA(cudaFuncSetAttribute(fft_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                      (int)(2 * (sizeof(cplx) << kMaxTileLog))));
+      attr_set = true;
+    }
     if (tw)
       fft_pass_kernel<true><<<grid, kFftThreads, smem, st>>>(base, s0, ns, logT, fft_stride,
                                                             sig_stride, tw, log_twN, sign);

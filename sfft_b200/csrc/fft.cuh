@@ -21,10 +21,13 @@ namespace sfftb {
 // only angles in [0, pi/4] reach libm (documented in DESIGN.md "twiddle rule").
 void host_twiddle(long k, long n, double *re, double *im);
 void host_twiddle_table(long n, cplx *out /* n/2 entries (>=1) */);
+// level-ordered copy of the same values, n-1 entries: level s (half-size h = 2^s)
+// at offset h-1 holds W_{2h}^k, k < h.  This is the layout the kernels read.
+void host_twiddle_levels(long n, cplx *out /* max(n-1, 1) entries */);
 
 // In-place DIT FFT over BIT-REVERSED input, natural-order output.
 //   element e of transform f of signal s lives at base[s*sig_stride + f*fft_stride + e]
-//   tw == nullptr -> twiddles from sincospi(); else table for size 2^log_twN >= N
+//   tw == nullptr -> twiddles from sincospi(); else LEVEL-ORDERED table for size 2^log_twN >= N
 //   sign = -1 forward, +1 backward (unnormalised)
 int fft_dit_inplace(cplx *base, int logN, int nfft, long long fft_stride, int nsig,
                     long long sig_stride, const cplx *tw, int log_twN, int sign,

@@ -12,6 +12,7 @@
 #include <vector>
 
 #include "fft.cuh"
+#include "v12_kernels.cuh"
 
 extern "C" {
 int sfftb_host_dolph_width(double lobefrac, double tolerance);
@@ -368,6 +369,7 @@ int build_filter(int logn, double lobefrac, double tolerance, int b, int fw_half
   if (fft_dit_inplace(d_G, logn, 1, n, 1, n, nullptr, 0, +1, st)) return -1;
   extract_taps_kernel<<<grid_for(w), kT, 0, st>>>(d_G, w, logn, out->time);
   SFFTB_LAUNCH_CHECK();
+  if (filter_refresh(out, st)) return -1;
   SFFTB_CUDA(cudaStreamSynchronize(st));
 
   cudaFree(d_samples); cudaFree(d_taps0); cudaFree(d_X);
@@ -376,12 +378,21 @@ int build_filter(int logn, double lobefrac, double tolerance, int b, int fw_half
   return 0;
 }
 
+int filter_refresh(DeviceFilter *f, cudaStream_t st)
+{
+  const int len = 2 * f->fw_half + 1;
+  if (!f->fdr) SFFTB_CUDA(cudaMalloc(&f->fdr, sizeof(double2) * len));
+  return launch_filter_den(f->fwin, len, f->fdr, st);
+}
+
 void free_filter(DeviceFilter *f)
 {
   if (f->time) cudaFree(f->time);
   if (f->fwin) cudaFree(f->fwin);
+  if (f->fdr) cudaFree(f->fdr);
   f->time = nullptr;
   f->fwin = nullptr;
+  f->fdr = nullptr;
 }
 
 }  // namespace sfftb

@@ -14,6 +14,7 @@ struct DeviceFilter {
   int fw_half = 0;       // fwin[m] = freq[(m - fw_half) mod n], m in [0, 2*fw_half]
   cplx *time = nullptr;  // [w]
   cplx *fwin = nullptr;  // [2*fw_half + 1]
+  double2 *fdr = nullptr; // [2*fw_half + 1]: (|f|^2, RN(1/|f|^2)), refreshed by filter_refresh()
 };
 
 // w for (lobefrac, tolerance)   (src/filters.cc:72-74)
@@ -24,6 +25,8 @@ int filter_width(double lobefrac, double tolerance);
 int build_filter(int logn, double lobefrac, double tolerance, int b, int fw_half, DeviceFilter *out,
                  cudaStream_t st);
 void free_filter(DeviceFilter *f);
+// recompute the derived tables after fwin changed (plan build, sfftb_set_filter)
+int filter_refresh(DeviceFilter *f, cudaStream_t st);
 
 // forward DFT of arbitrary length (device in/out)
 int bluestein_forward(const cplx *d_x, int w, cplx *d_out, cudaStream_t st);

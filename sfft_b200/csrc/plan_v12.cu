@@ -164,8 +164,8 @@ int v12_build(PlanImpl *p)
   int twN = v.B_loc > v.B_est ? v.B_loc : v.B_est;
   if (v.with_comb && v.W_Comb > twN) twN = v.W_Comb;
   v.log_twN = ilog2((unsigned)twN);
-  std::vector<cplx> tw((size_t)(twN / 2 > 0 ? twN / 2 : 1));
-  host_twiddle_table(twN, tw.data());
+  std::vector<cplx> tw((size_t)(twN > 1 ? twN - 1 : 1));
+  host_twiddle_levels(twN, tw.data());
   SFFTB_CUDA(cudaMalloc(&v.d_tw, sizeof(cplx) * tw.size()));
   SFFTB_CUDA(cudaMemcpyAsync(v.d_tw, tw.data(), sizeof(cplx) * tw.size(), cudaMemcpyHostToDevice, st));
   SFFTB_CUDA(cudaStreamSynchronize(st));
@@ -381,6 +381,7 @@ int v12_exec(PlanImpl *p, const cplx *d_in, long long stride, int nsig, const sf
   ea.xs = v.d_xs; ea.xs_stride = v.x_samp_size;
   ea.fwin[0] = v.filt[0].fwin; ea.fwin[1] = v.filt[1].fwin;
   ea.fw_half[0] = v.filt[0].fw_half; ea.fw_half[1] = v.filt[1].fw_half;
+  ea.fdr[0] = v.filt[0].fdr; ea.fdr[1] = v.filt[1].fdr;
   ea.hits = v.d_voted; ea.hits_cap = v.max_voted;
   ea.count = v.d_voted_count;
   ea.approved = v.with_comb ? v.d_approved : nullptr;

@@ -85,21 +85,25 @@ int launch_gather(const LoopGeom &g, const GatherArgs &a, int nloops, int nsig, 
 // K3+K4  |.|^2 and top-num bucket selection   (cf12.cc:278-302, utils.cc:131-158)
 //
 // One CTA per (row, signal).  Squared magnitudes become order-preserving 64-bit
-// keys; an MSD radix select (8 digits of 8 bits, run-length-aggregated shared
-// atomics) finds the (num+1)-th largest key = the reference's cutoff; then an
-// ordered compaction emits indices with key > cutoff and, if short, the first
-// few with key == cutoff -- the reference's tie rule -- ascending, together with a
-// B-bit membership bitmap for the voting stage.
+// keys held in shared memory (padded against bank conflicts); an MSD radix select
+// (8 digits of 8 bits, run-length-aggregated shared atomics) finds the
+// (num+1)-th largest key = the reference's cutoff.  Every thread owns a contiguous
+// chunk of bucket indices, so ONE block-wide scan of (count > cutoff, count ==
+// cutoff) places its selections: indices with key > cutoff and, if short, the first
+// few with key == cutoff -- the reference's tie rule -- come out ascending, together
+// with a B-bit membership bitmap for the voting stage.
 // ---------------------------------------------------------------------------
 constexpr int kSelectThreads = 1024;
-constexpr int kSelectSmemKeys = 16384;   // 128 KB of keys in shared memory
+constexpr int kSelectSmemKeys = 16384;   // rows up to this size keep their keys in shared memory
+
+__device__ __forceinline__ int key_slot(int i, bool padded) { return padded ? i + (i >> 4) : i; }
 
 __global__ void __launch_bounds__(kSelectThreads)
 select_kernel(SelectArgs a)
 {
-  extern __shared__ unsigned long long skeys[];
+  extern __shared__ unsigned long long sel_smem[];
   __shared__ unsigned hist[256];
-  __shared__ unsigned warp_gt[32], warp_eq[32];
+  __shared__ unsigned long long warp_tot[32];
   __shared__ unsigned long long sh_prefix;
   __shared__ unsigned sh_K;
 
@@ -107,13 +111,24 @@ select_kernel(SelectArgs a)
   const int s = blockIdx.y;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int B = 1 << a.logB;
+  const int words = B >= 32 ? B / 32 : 1;
+  const bool in_smem = a.gkeys == nullptr;
   const cplx *__restrict__ src = a.xs + (long long)s * a.xs_stride + (long long)row * a.row_stride;
+  // dynamic shared memory: [bitmap words (rounded to 8 B)] [padded keys, if they fit]
+  unsigned *bm_s = reinterpret_cast<unsigned *>(sel_smem);
   unsigned long long *keys =
-      a.gkeys ? a.gkeys + (long long)s * a.gk_sig_stride + (long long)row * B : skeys;
+      in_smem ? sel_smem + (words + 1) / 2
+              : a.gkeys + (long long)s * a.gk_sig_stride + (long long)row * B;
 
   for (int i = tid; i < B; i += kSelectThreads)
-    keys[i] = (unsigned long long)__double_as_longlong(cabs2_rn(src[i]));
+    keys[key_slot(i, in_smem)] = (unsigned long long)__double_as_longlong(cabs2_rn(src[i]));
+  for (int i = tid; i < words; i += kSelectThreads) bm_s[i] = 0u;
   __syncthreads();
+
+  // contiguous ownership: thread t holds indices [t*E, (t+1)*E)
+  const int E = B >= kSelectThreads ? B / kSelectThreads : 1;
+  const int lo = tid * E;
+  const int mine = lo < B ? E : 0;
 
   unsigned long long prefix = 0;
   unsigned K = (unsigned)a.num + 1u;      // rank from the top of the wanted key
@@ -123,8 +138,8 @@ select_kernel(SelectArgs a)
     __syncthreads();
     int run_d = -1;
     unsigned run_c = 0;
-    for (int i = tid; i < B; i += kSelectThreads) {
-      const unsigned long long key = keys[i];
+    for (int e = 0; e < mine; e++) {
+      const unsigned long long key = keys[key_slot(lo + e, in_smem)];
       const bool match = pass == 0 ? true : ((key >> (shift + 8)) == prefix);
       if (match) {
         const int d = (int)((key >> shift) & 255ull);
@@ -174,57 +189,75 @@ select_kernel(SelectArgs a)
   const unsigned long long cutoff = prefix;
   const unsigned need = K - 1u;   // ties at the cutoff to admit, in index order
 
-  int *J = a.J + (long long)s * a.J_sig_stride + (long long)row * a.num;
-  const int words = B >= 32 ? B / 32 : 1;
-  unsigned *bm = a.bitmap + (long long)s * a.bm_sig_stride + (long long)row * words;
-  unsigned base_gt = 0, base_eq = 0;
-  for (int base = 0; base < B; base += kSelectThreads) {
-    const int i = base + tid;
-    const bool valid = i < B;
-    const unsigned long long key = valid ? keys[i] : 0ull;
-    const bool f_gt = valid && key > cutoff;
-    const bool f_eq = valid && key == cutoff;
-    const unsigned bal_gt = __ballot_sync(0xffffffffu, f_gt);
-    const unsigned bal_eq = __ballot_sync(0xffffffffu, f_eq);
-    if (lane == 0) {
-      warp_gt[warp] = __popc(bal_gt);
-      warp_eq[warp] = __popc(bal_eq);
-    }
-    __syncthreads();
-    unsigned off_gt = 0, off_eq = 0, tot_gt = 0, tot_eq = 0;
-    for (int wv = 0; wv < kSelectThreads / 32; wv++) {
-      const unsigned g_ = warp_gt[wv], e_ = warp_eq[wv];
-      if (wv < warp) { off_gt += g_; off_eq += e_; }
-      tot_gt += g_;
-      tot_eq += e_;
-    }
-    const unsigned lt = (1u << lane) - 1u;
-    const unsigned gt_before = base_gt + off_gt + __popc(bal_gt & lt);
-    const unsigned eq_before = base_eq + off_eq + __popc(bal_eq & lt);
-    const bool sel = f_gt || (f_eq && eq_before < need);
-    if (sel) J[gt_before + (eq_before < need ? eq_before : need)] = i;
-    const unsigned bal_sel = __ballot_sync(0xffffffffu, sel);
-    if (lane == 0 && base + 32 * warp < B)
-      bm[(base >> 5) + warp] = bal_sel;
-    base_gt += tot_gt;
-    base_eq += tot_eq;
-    __syncthreads();
+  // per-thread counts over the owned chunk, packed (gt << 32 | eq), then one block scan
+  unsigned long long cnt = 0;
+  for (int e = 0; e < mine; e++) {
+    const unsigned long long key = keys[key_slot(lo + e, in_smem)];
+    cnt += key > cutoff ? (1ull << 32) : (key == cutoff ? 1ull : 0ull);
   }
+  unsigned long long incl = cnt;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += v;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const unsigned long long t = warp_tot[lane];
+    unsigned long long sc = t;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const unsigned long long v = __shfl_up_sync(0xffffffffu, sc, off);
+      if (lane >= off) sc += v;
+    }
+    warp_tot[lane] = sc - t;     // exclusive prefix of warp totals
+  }
+  __syncthreads();
+  const unsigned long long before = warp_tot[warp] + incl - cnt;
+  unsigned gt_b = (unsigned)(before >> 32), eq_b = (unsigned)(before & 0xffffffffu);
+
+  int *J = a.J + (long long)s * a.J_sig_stride + (long long)row * a.num;
+  for (int e = 0; e < mine; e++) {
+    const int i = lo + e;
+    const unsigned long long key = keys[key_slot(i, in_smem)];
+    const bool f_gt = key > cutoff, f_eq = key == cutoff;
+    if (f_gt || (f_eq && eq_b < need)) {
+      J[gt_b + (eq_b < need ? eq_b : need)] = i;
+      atomicOr(&bm_s[i >> 5], 1u << (i & 31));
+    }
+    gt_b += f_gt;
+    eq_b += f_eq;
+  }
+  __syncthreads();
+  unsigned *bm = a.bitmap + (long long)s * a.bm_sig_stride + (long long)row * words;
+  for (int i = tid; i < words; i += kSelectThreads) bm[i] = bm_s[i];
+}
+
+static size_t select_smem_bytes(int B, bool keys_in_smem)
+{
+  const int words = B >= 32 ? B / 32 : 1;
+  size_t bytes = (size_t)((words + 1) / 2) * 8;
+  if (keys_in_smem) bytes += (size_t)(B + (B >> 4) + 1) * 8;
+  return bytes;
 }
 
 int launch_select(const SelectArgs &a, int nrows, int nsig, cudaStream_t st)
 {
   if (nrows <= 0) return 0;
   const int B = 1 << a.logB;
-  size_t smem = a.gkeys ? 0 : (size_t)B * sizeof(unsigned long long);
+  if (!a.gkeys && B > kSelectSmemKeys) {
+    set_error("launch_select: rows above 16384 buckets need the global key scratch");
+    return -1;
+  }
   static bool attr_set = false;
   if (!attr_set) {
     SFFTB_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    kSelectSmemKeys * (int)sizeof(unsigned long long)));
+                                    (int)select_smem_bytes(kSelectSmemKeys, true)));
     attr_set = true;
   }
   dim3 grid((unsigned)nrows, (unsigned)nsig);
-  select_kernel<<<grid, kSelectThreads, smem, st>>>(a);
+  select_kernel<<<grid, kSelectThreads, select_smem_bytes(B, a.gkeys == nullptr), st>>>(a);
   SFFTB_LAUNCH_CHECK();
   return 0;
 }
@@ -356,11 +389,156 @@ __device__ __forceinline__ void estimate_term(const LoopGeom &g, const EstimateA
   out_im = __ddiv_rn(__dsub_rn(ad, bc), den);              // :390-392: (a*d) + (-(b*c))
 }
 
-// L > 0: loop count known at compile time, everything in registers.
-// L == 0: generic fallback (loop count at run time, values in local memory).
+// a / b with y = RN(1/b) precomputed: two Markstein correction steps give the
+// correctly rounded quotient (== __ddiv_rn) whenever nothing under/overflows; outside
+// a wide safe exponent band, and for a == 0 (sign of zero), take the real division.
+// Checked against __ddiv_rn by sfftb_debug_div_check (tests/test_gpu_stages.py).
+__device__ __forceinline__ double div_by_rcp_rn(double a, double b, double y)
+{
+  const unsigned ea = ((unsigned)__double2hiint(a) >> 20) & 0x7ffu;
+  const unsigned eb = ((unsigned)__double2hiint(b) >> 20) & 0x7ffu;
+  if (ea - 640u < 768u && eb - 640u < 768u) {      // 2^-383 <= |a|,|b| < 2^385
+    double q = __dmul_rn(a, y);
+    double r = __fma_rn(-b, q, a);
+    q = __fma_rn(r, y, q);
+    r = __fma_rn(-b, q, a);
+    q = __fma_rn(r, y, q);
+    return q;
+  }
+  return __ddiv_rn(a, b);
+}
+
+// (den, RN(1/den)) for every entry of a filter-response window
+__global__ void filter_den_kernel(const cplx *__restrict__ fwin, int len, double2 *fdr)
+{
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= len) return;
+  const cplx f = fwin[i];
+  const double den = __dadd_rn(__dmul_rn(f.x, f.x), __dmul_rn(f.y, f.y));   // cf12.cc:394-396
+  fdr[i] = make_double2(den, __drcp_rn(den));
+}
+
+int launch_filter_den(const cplx *fwin, int len, double2 *fdr, cudaStream_t st)
+{
+  filter_den_kernel<<<ceil_div(len, 256), 256, 0, st>>>(fwin, len, fdr);
+  SFFTB_LAUNCH_CHECK();
+  return 0;
+}
+
+__global__ void div_check_kernel(unsigned long long seed, long long count, unsigned long long *mismatch)
+{
+  unsigned long long bad = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < count;
+       i += (long long)gridDim.x * blockDim.x) {
+    // splitmix64 -> two doubles with random mantissas, exponents spread over +-40 binades
+    unsigned long long z = seed + 0x9E3779B97F4A7C15ull * (unsigned long long)(i + 1);
+    unsigned long long r[2];
+    for (int q = 0; q < 2; q++) {
+      z += 0x9E3779B97F4A7C15ull;
+      unsigned long long t = z;
+      t = (t ^ (t >> 30)) * 0xBF58476D1CE4E5B9ull;
+      t = (t ^ (t >> 27)) * 0x94D049BB133111EBull;
+      r[q] = t ^ (t >> 31);
+    }
+    const int ex_a = (int)((r[0] >> 52) % 81) - 40, ex_b = (int)((r[1] >> 52) % 81) - 40;
+    unsigned long long ma = r[0] & 0xFFFFFFFFFFFFFull, mb = r[1] & 0xFFFFFFFFFFFFFull;
+    if ((i & 15) == 0) mb = (i & 16) ? 0xFFFFFFFFFFFFFull : 0ull;       // all-ones / power-of-two divisors
+    if ((i & 31) == 1) ma = mb;                                          // equal mantissas
+    double a = __longlong_as_double((long long)(((unsigned long long)(1023 + ex_a) << 52) | ma));
+    const double b = __longlong_as_double((long long)(((unsigned long long)(1023 + ex_b) << 52) | mb));
+    if (r[0] >> 63) a = -a;
+    const double y = __drcp_rn(b);
+    const double q1 = div_by_rcp_rn(a, b, y), q2 = __ddiv_rn(a, b);
+    bad += __double_as_longlong(q1) != __double_as_longlong(q2);
+  }
+  if (bad) atomicAdd(mismatch, bad);
+}
+
+long long run_div_check(unsigned long long seed, long long count)
+{
+  unsigned long long *d = nullptr, h = 0;
+  if (cudaMalloc(&d, 8) != cudaSuccess) return -1;
+  cudaMemset(d, 0, 8);
+  div_check_kernel<<<148 * 8, 256>>>(seed, count, d);
+  g_launches++;
+  if (cudaMemcpy(&h, d, 8, cudaMemcpyDeviceToHost) != cudaSuccess) { cudaFree(d); return -1; }
+  cudaFree(d);
+  return (long long)h;
+}
+
+// Estimation kernel, L loops known at compile time.  Two adjacent lanes share one
+// hit: the even lane carries the L real parts, the odd lane the L imaginary parts;
+// each keeps its L quotients in registers and runs one median network.  Both lanes
+// read the same bucket / filter entries (one memory transaction per pair).
 template <int L>
+__global__ void __launch_bounds__(256, 2)
+estimate_pair_kernel(LoopGeom g, EstimateArgs a, long long max_per_sig)
+{
+  const int s = blockIdx.y;
+  long long total;
+  int nc = 1;
+  if (a.approved) {
+    nc = a.num_comb[s];
+    total = (long long)nc * a.n_over_W;
+    if (nc < 1) nc = 1;
+  } else {
+    total = a.count[s];
+  }
+  if (total > max_per_sig) total = max_per_sig;
+  const int *__restrict__ perm = a.perm + (long long)s * perm_stride(g.loops) + g.loops;   // ai[]
+  const cplx *__restrict__ xs = a.xs + (long long)s * a.xs_stride;
+  const bool imag = threadIdx.x & 1;
+  const int pair = threadIdx.x >> 1;
+  const unsigned mask = (unsigned)g.n_mask;
+
+  for (long long base = (long long)blockIdx.x * 128; base < total; base += (long long)gridDim.x * 128) {
+    const long long h = base + pair;
+    const bool active = h < total;
+    const long long hc = active ? h : total - 1;
+    unsigned loc;
+    if (a.approved) {
+      const long long jj = hc / nc;
+      const int i = (int)(hc - jj * nc);
+      loc = (unsigned)(jj * a.W + __ldg(&a.approved[(long long)s * a.approved_stride + i]));   // cf12.cc:508-511
+    } else {
+      loc = (unsigned)a.hits[(long long)s * a.hits_cap + hc];
+    }
+    double v[L];
+#pragma unroll
+    for (int j = 0; j < L; j++) {
+      const bool est = j >= g.loops_loc;
+      const int logB = est ? g.logB[1] : g.logB[0];
+      const int logseg = g.logn - logB;
+      const int seg = 1 << logseg;
+      const unsigned pos = (unsigned)(((unsigned long long)(unsigned)__ldg(&perm[j]) * loc) & mask);   // cf12.cc:370
+      unsigned bucket = pos >> logseg;
+      int dist = (int)(pos & (unsigned)(seg - 1));
+      if (dist > seg / 2) {                                                                 // :373-377
+        bucket = (bucket + 1) & ((1u << logB) - 1u);
+        dist -= seg;
+      }
+      const cplx sv = xs[loop_offset(g, j) + bucket];
+      const int fi = (est ? a.fw_half[1] : a.fw_half[0]) - dist;                           // freq[(n - dist) % n]
+      const cplx f = __ldg(&(est ? a.fwin[1] : a.fwin[0])[fi]);
+      const double2 dr = __ldg(&(est ? a.fdr[1] : a.fdr[0])[fi]);
+      // even lane: (a*c + b*d) / den      odd lane: (a*d - b*c) / den   (:388-398)
+      const double t1 = __dmul_rn(sv.x, imag ? f.y : f.x);
+      const double t2 = __dmul_rn(sv.y, imag ? f.x : f.y);
+      const double num = __dadd_rn(t1, imag ? -t2 : t2);
+      v[j] = div_by_rcp_rn(num, dr.x, dr.y);
+    }
+    const double mine = MedianNet<L>::run(v);                                               // :406-412
+    const double other = __shfl_xor_sync(0xffffffffu, mine, 1);
+    if (active && !imag) {
+      a.out_loc[(long long)s * a.out_cap + h] = (int)loc;
+      a.out_val[(long long)s * a.out_cap + h] = make_double2(mine, other);
+    }
+  }
+}
+
+// generic fallback: loop count at run time, values in local memory, plain division
 __global__ void __launch_bounds__(128)
-estimate_kernel(LoopGeom g, EstimateArgs a, long long max_per_sig)
+estimate_generic_kernel(LoopGeom g, EstimateArgs a, long long max_per_sig)
 {
   const int s = blockIdx.y;
   long long total;
@@ -372,46 +550,27 @@ estimate_kernel(LoopGeom g, EstimateArgs a, long long max_per_sig)
     total = a.count[s];
   }
   if (total > max_per_sig) total = max_per_sig;
-  const int loops = L > 0 ? L : g.loops;
+  const int loops = g.loops;
   const int mid = (loops - 1) / 2;     // cf12.cc:406
   const int *__restrict__ perm = a.perm + (long long)s * perm_stride(g.loops) + g.loops;   // ai[]
   const cplx *__restrict__ xs = a.xs + (long long)s * a.xs_stride;
-
   for (long long h = blockIdx.x * (long long)blockDim.x + threadIdx.x; h < total;
        h += (long long)gridDim.x * blockDim.x) {
     unsigned loc;
     if (a.approved) {
       const long long jj = h / nc;
       const int i = (int)(h - jj * nc);
-      loc = (unsigned)(jj * a.W + __ldg(&a.approved[(long long)s * a.approved_stride + i]));   // cf12.cc:508-511
+      loc = (unsigned)(jj * a.W + __ldg(&a.approved[(long long)s * a.approved_stride + i]));
     } else {
       loc = (unsigned)a.hits[(long long)s * a.hits_cap + h];
     }
-    double re, im;
-    if (L > 0) {
-      double vr[L > 0 ? L : 2], vi[L > 0 ? L : 2];
-#pragma unroll
-      for (int j = 0; j < (L > 0 ? L : 2); j++)
-        estimate_term(g, a, xs, (unsigned)__ldg(&perm[j]), loc, j, vr[j], vi[j]);
-      re = MedianNet<(L > 0 ? L : 2)>::run(vr);
-      im = MedianNet<(L > 0 ? L : 2)>::run(vi);
-    } else {
-      double vr[kMaxLoops], vi[kMaxLoops];
-      for (int j = 0; j < loops; j++)
-        estimate_term(g, a, xs, (unsigned)perm[j], loc, j, vr[j], vi[j]);
-      re = select_rank(vr, loops, mid);
-      im = select_rank(vi, loops, mid);
-    }
+    double vr[kMaxLoops], vi[kMaxLoops];
+    for (int j = 0; j < loops; j++)
+      estimate_term(g, a, xs, (unsigned)perm[j], loc, j, vr[j], vi[j]);
     a.out_loc[(long long)s * a.out_cap + h] = (int)loc;
-    a.out_val[(long long)s * a.out_cap + h] = make_double2(re, im);
+    a.out_val[(long long)s * a.out_cap + h] =
+        make_double2(select_rank(vr, loops, mid), select_rank(vi, loops, mid));
   }
-}
-
-template <int L>
-static void launch_estimate_t(const LoopGeom &g, const EstimateArgs &a, dim3 grid, long long max_per_sig,
-                              cudaStream_t st)
-{
-  estimate_kernel<L><<<grid, 128, 0, st>>>(g, a, max_per_sig);
 }
 
 int launch_estimate(const LoopGeom &g, const EstimateArgs &a, int nsig, long long max_per_sig,
@@ -423,16 +582,18 @@ int launch_estimate(const LoopGeom &g, const EstimateArgs &a, int nsig, long lon
   if (blocks < 1) blocks = 1;
   dim3 grid((unsigned)blocks, (unsigned)nsig);
   switch (g.loops) {
-#define SFFTB_EST_CASE(N) case N: launch_estimate_t<N>(g, a, grid, max_per_sig, st); break;
-    // every total loop count of the reference's tables (parameters.cc) and defaults
+#define SFFTB_EST_CASE(N) case N: estimate_pair_kernel<N><<<grid, 256, 0, st>>>(g, a, max_per_sig); break;
     SFFTB_EST_CASE(2) SFFTB_EST_CASE(3) SFFTB_EST_CASE(4) SFFTB_EST_CASE(5) SFFTB_EST_CASE(6)
     SFFTB_EST_CASE(7) SFFTB_EST_CASE(8) SFFTB_EST_CASE(9) SFFTB_EST_CASE(10)
+    // every total loop count of the reference's tables (parameters.cc) and defaults
     SFFTB_EST_CASE(11) SFFTB_EST_CASE(12) SFFTB_EST_CASE(13) SFFTB_EST_CASE(14)
     SFFTB_EST_CASE(15) SFFTB_EST_CASE(16) SFFTB_EST_CASE(17) SFFTB_EST_CASE(18)
     SFFTB_EST_CASE(19) SFFTB_EST_CASE(20) SFFTB_EST_CASE(21) SFFTB_EST_CASE(22)
-    SFFTB_EST_CASE(23) SFFTB_EST_CASE(24)
+    SFFTB_EST_CASE(23) SFFTB_EST_CASE(24) SFFTB_EST_CASE(25) SFFTB_EST_CASE(26)
+    SFFTB_EST_CASE(27) SFFTB_EST_CASE(28) SFFTB_EST_CASE(29) SFFTB_EST_CASE(30)
+    SFFTB_EST_CASE(31) SFFTB_EST_CASE(32)
 #undef SFFTB_EST_CASE
-    default: launch_estimate_t<0>(g, a, grid, max_per_sig, st); break;
+    default: estimate_generic_kernel<<<grid, 128, 0, st>>>(g, a, max_per_sig); break;
   }
   SFFTB_LAUNCH_CHECK();
   return 0;

@@ -58,6 +58,7 @@ struct EstimateArgs {
   const int *perm;
   const cplx *xs;       long long xs_stride;
   const cplx *fwin[2];  int fw_half[2];
+  const double2 *fdr[2];                 // (|f|^2, RN(1/|f|^2)) per window entry
   // v1: explicit hit list;  v2: implicit prefill list (jj*W + approved[i])
   const int *hits;      long long hits_cap;
   const int *count;
@@ -70,6 +71,8 @@ int launch_select(const SelectArgs &a, int nrows, int nsig, cudaStream_t st);
 int launch_vote(const LoopGeom &g, const VoteArgs &a, int nsig, cudaStream_t st);
 int launch_estimate(const LoopGeom &g, const EstimateArgs &a, int nsig, long long max_per_sig,
                     cudaStream_t st);
+int launch_filter_den(const cplx *fwin, int len, double2 *fdr, cudaStream_t st);
+long long run_div_check(unsigned long long seed, long long count);
 
 // v2: xs[c][bitrev(i)] = x[offset_c + i*sigma]   (cf12.cc:61-67)
 int launch_comb_sample(const cplx *x, long long x_stride, const int *comb_off, int comb_loops,

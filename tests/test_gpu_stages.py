@@ -69,3 +69,12 @@ def test_top_num_selection_matches_find_largest_indices(L, oracle_mod, B, num):
     for b in range(batch):
         want = oracle_mod.find_largest_indices(v[b] * v[b], num)
         assert np.array_equal(out[b], want), f"row {b}"
+
+
+def test_reciprocal_division_is_ieee_exact(L):
+    """The estimation kernel divides by a precomputed RN(1/den) plus two correction
+    steps; it must equal IEEE division bit for bit (2^31 pseudo-random operand pairs,
+    including all-ones / power-of-two divisors and equal mantissas)."""
+    for seed in (1, 2):
+        bad = L.sfftb_debug_div_check(seed, 1 << 30)
+        assert bad == 0, f"{bad} quotients differ from __ddiv_rn"

@@ -80,6 +80,14 @@ __global__ void fill_kernel(double2 *x, long long n)
 
 int main(int argc, char **argv)
 {
+  // optional: L2 fetch granularity hint in bytes (32, 64 or 128)
+  if (argc > 1) {
+    size_t g = (size_t)atoi(argv[1]);
+    CK(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g));
+  }
+  size_t gran = 0;
+  CK(cudaDeviceGetLimit(&gran, cudaLimitMaxL2FetchGranularity));
+  printf("{\"l2_fetch_granularity\": %zu}\n", gran);
   const int logs[] = {22, 24, 26, 27};
   double2 *sink; CK(cudaMalloc(&sink, 64));
   char *flush; const size_t flush_bytes = 512ull << 20; CK(cudaMalloc(&flush, flush_bytes));
