@@ -115,6 +115,7 @@ sfft_plan *sfft_make_plan(int n, int k, sfft_version version, int fftw_optimizat
     fprintf(stderr, "[libsfft] FATAL: no CUDA device visible; libsfft.so has no CPU fallback\n");
     return nullptr;
   }
+  cudaGetLastError();   // drop any stale, non-sticky error left by the caller's earlier CUDA calls
   PlanImpl *p = new PlanImpl();
   if (cudaGetDevice(&p->device) != cudaSuccess) { delete p; return nullptr; }
   if (cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -297,6 +298,7 @@ int sfftb_exec_many_device(sfft_plan *plan, int num, const void *d_in, long long
   PlanImpl *p = impl(plan);
   if (!p || !d_in || num <= 0) { set_error("sfftb_exec_many_device: bad argument"); return -1; }
   if (bind_device(p)) return -1;
+  cudaGetLastError();   // stale errors of the caller must not be mistaken for launch failures
   std::vector<sfftb_draw> local;
   if (!draws) {
     local.resize((size_t)num);

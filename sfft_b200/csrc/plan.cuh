@@ -63,7 +63,7 @@ struct PlanV12 {
   int *d_stage = nullptr;          // [cap * ints_per_sig]
   int ints_per_sig = 0;
   int *h_stage[kStageSlots] = {nullptr};
-  cudaEvent_t stage_ev[kStageSlots];
+  cudaEvent_t stage_ev[kStageSlots] = {nullptr};
   int stage_next = 0;
   long long *h_counts = nullptr;   // pinned
 };

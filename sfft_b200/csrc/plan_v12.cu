@@ -255,7 +255,10 @@ void v12_free(PlanImpl *p)
   free_filter(&v.filt[1]);
   cudaFree(v.d_tw);
   v.d_tw = nullptr;
-  for (int i = 0; i < kStageSlots; i++) cudaEventDestroy(v.stage_ev[i]);
+  for (int i = 0; i < kStageSlots; i++) {
+    if (v.stage_ev[i]) cudaEventDestroy(v.stage_ev[i]);
+    v.stage_ev[i] = nullptr;
+  }
 }
 
 // One transform's worth of libc randomness, in the reference's order:

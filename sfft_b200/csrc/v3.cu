@@ -1,18 +1,892 @@
-// v3.cu -- sFFT v3 (exact-sparse) on the device.  Placeholder until the kernels land.
+// v3.cu -- sFFT v3 (exact-sparse) on the device.
+//
+// Reference: alternate_fft and helpers, src/computefourier-3.0.cc:66-1088; plan in
+// src/sfft.cc:506-579.  The reference is a strictly sequential peeling loop on one
+// CPU thread.  Here:
+//   * the three bucketisations (aliasing "Mansour" subsample, contiguous window,
+//     permuted window) are grids over (bucket, shift), followed by the shared
+//     tiled FFT passes;
+//   * everything after that -- decode every bucket, append to the result, peel the
+//     found coefficients out of all three bucket arrays, repeat until the occupied
+//     bucket counts stop changing -- is ONE persistent CTA per signal: each round
+//     decodes all buckets in parallel (ordered compaction keeps the reference's
+//     ascending-bucket order), turns every found coefficient into its 14 bucket
+//     deltas in parallel, and applies the deltas per bucket in item order (short
+//     linked lists), so the result is deterministic and independent of thread timing.
+//
+// Bucket arrays are planar here, S[shift][bucket]; the reference interleaves them,
+// S[2*bucket + shift] (FFTW stride-2 plans, sfft.cc:434-475).
+//
+// libm (atan2, sincos, sqrt) is CUDA's, not glibc's: v3 parity is "same locations,
+// values to 1e-9", not bit-identity.
+#include <math.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "fft.cuh"
 #include "plan.cuh"
 
 namespace sfftb {
 
-struct PlanV3 { int dummy; };
+int mod_inverse_pub(int a, int n);
+int gcd_pub(int a, int b);
 
-int v3_build(PlanImpl *, int, int) { set_error("sFFT v3 is not built yet in this library"); return -1; }
-void v3_free(PlanImpl *) {}
-int v3_draw(const PlanImpl *, sfftb_draw *) { set_error("v3 not built"); return -1; }
-int v3_exec(PlanImpl *, const cplx *, long long, int, const sfftb_draw *) { set_error("v3 not built"); return -1; }
-int v3_info(const PlanImpl *, sfftb_info *) { set_error("v3 not built"); return -1; }
-int v3_result(PlanImpl *, const int **, const cplx **, const int **, long long *) { set_error("v3 not built"); return -1; }
-int v3_filter_sizes(const PlanImpl *, int, int *, int *) { return -1; }
-DeviceFilter *v3_filter(PlanImpl *, int) { return nullptr; }
-long long v3_debug_fetch(PlanImpl *, const char *, void *, size_t) { return -1; }
+struct PlanV3 {
+  int W_Man = 0, B_g1 = 0, B_g2 = 0;
+  int logW = 0, logB1 = 0, logB2 = 0;
+  DeviceFilter filt[2];            // [0] first (contiguous) window, [1] second (permuted) window
+  cplx *d_tw = nullptr;
+  int log_twN = 0;
+  int cap = 0;                     // signals
+  // per-signal scratch
+  long long nslots = 0;            // 2*B2 + 2*B1 + 2*W
+  int est_cap = 0, ans_cap = 0, tgt_cap = 0, hash_size = 0, log_hash = 0;
+  cplx *d_samp = nullptr;          // [cap][nslots]: G2 planes, G1 planes, MAN planes
+  int *d_head = nullptr;           // [cap][nslots]
+  int *d_est_key = nullptr;        // [cap][est_cap]
+  cplx *d_est_val = nullptr;       // [cap][est_cap]
+  int *d_t_slot = nullptr;         // [cap][tgt_cap*14], tgt_cap = max(est_cap, ans_cap)
+  int *d_t_next = nullptr;
+  cplx *d_t_delta = nullptr;
+  int *d_hkey = nullptr, *d_hidx = nullptr;   // [cap][hash_size]
+  int *d_ans_key = nullptr;        // [cap][ans_cap]
+  cplx *d_ans_val = nullptr;       // [cap][ans_cap]
+  int *d_count = nullptr;          // [cap]
+  int *d_rounds = nullptr;         // [cap]
+  int *d_draw = nullptr;           // [cap][8]
+  int *h_draw[kStageSlots] = {nullptr};
+  cudaEvent_t ev[kStageSlots] = {nullptr};
+  int next_slot = 0;
+};
+
+namespace {
+
+struct V3Geom {
+  int n, logn, k;
+  int W, logW, B1, logB1, B2, logB2;
+  int w1, w2;
+  int fw_half1, fw_half2;
+  long long nslots;
+  int est_cap, ans_cap, tgt_cap, hash_size, log_hash;
+};
+
+// draw layout per signal: a, ai, b, shift, init_offset, init_G_offset
+enum { D_A = 0, D_AI, D_B, D_SHIFT, D_OFF, D_GOFF, D_INTS = 8 };
+
+__device__ __forceinline__ int g2_base(const V3Geom &g) { (void)g; return 0; }
+__device__ __forceinline__ int g1_base(const V3Geom &g) { return 2 * g.B2; }
+__device__ __forceinline__ int man_base(const V3Geom &g) { return 2 * g.B2 + 2 * g.B1; }
+
+// ---- bucketisation kernels -------------------------------------------------
+
+// x_man[shift][i] = x[(off + shift + i*sigma) mod n]   (computefourier-3.0.cc:111-121)
+__global__ void v3_mansour_kernel(V3Geom g, const cplx *__restrict__ x, long long x_stride,
+                                  const int *__restrict__ draw, cplx *samp)
+{
+  const int s = blockIdx.z, l = blockIdx.y;
+  const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (unsigned)g.W) return;
+  const int off = draw[s * D_INTS + D_OFF];
+  const unsigned idx = ((unsigned)off + (unsigned)l + (i << (g.logn - g.logW))) & (unsigned)(g.n - 1);
+  samp[(long long)s * g.nslots + man_base(g) + l * g.W + bitrev(i, g.logW)] =
+      ldg_stream(x + (long long)s * x_stride + idx);
+}
+
+// contiguous window: S[l][b] = sum_c x[(G + cB + b + l) mod n] * taps[cB + b], c < floor(w/B)
+// (computefourier-3.0.cc:155-202)
+__global__ void v3_gauss_kernel(V3Geom g, const cplx *__restrict__ x, long long x_stride,
+                                const int *__restrict__ draw, const cplx *__restrict__ taps, cplx *samp)
+{
+  const int s = blockIdx.z, l = blockIdx.y;
+  const unsigned b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= (unsigned)g.B1) return;
+  const unsigned G = (unsigned)draw[s * D_INTS + D_GOFF];
+  const int chunks = g.w1 / g.B1;
+  const cplx *__restrict__ xs = x + (long long)s * x_stride;
+  double ar = 0.0, ai = 0.0;
+  for (int c = 0; c < chunks; c++) {
+    const unsigned t = (unsigned)c * g.B1 + b;
+    const cplx v = xs[(G + t + l) & (unsigned)(g.n - 1)];
+    const cplx f = __ldg(&taps[t]);
+    // (c*a - d*b, d*a + c*b) with c+di the tap   (:179-185)
+    ar = __dadd_rn(ar, __dsub_rn(__dmul_rn(f.x, v.x), __dmul_rn(f.y, v.y)));
+    ai = __dadd_rn(ai, __dadd_rn(__dmul_rn(f.y, v.x), __dmul_rn(f.x, v.y)));
+  }
+  samp[(long long)s * g.nslots + g1_base(g) + l * g.B1 + bitrev(b, g.logB1)] = make_double2(ar, ai);
+}
+
+__device__ __forceinline__ cplx cpow_int(cplx base, unsigned e)
+{
+  cplx r = make_double2(1.0, 0.0);
+  while (e) {
+    if (e & 1u) r = cmul_rn(r, base);
+    base = cmul_rn(base, base);
+    e >>= 1;
+  }
+  return r;
+}
+
+// permuted window: P[i] = x[(G + i*ai) mod n] * e^{2 pi i (G + i*ai) b / n} (:66-87, the reference
+// runs the phase as a running product); S[l][bk] = sum_c P[cB + bk + l] * taps[cB + bk] (:245-287)
+__global__ void v3_gauss_perm_kernel(V3Geom g, const cplx *__restrict__ x, long long x_stride,
+                                     const int *__restrict__ draw, const cplx *__restrict__ taps, cplx *samp)
+{
+  const int s = blockIdx.z, l = blockIdx.y;
+  const unsigned bk = blockIdx.x * blockDim.x + threadIdx.x;
+  if (bk >= (unsigned)g.B2) return;
+  const int *d = draw + s * D_INTS;
+  const int G = d[D_GOFF], ai = d[D_AI], b = d[D_B];
+  const double nn = (double)g.n;
+  // same expression order as the reference so the (large) arguments round identically
+  const double arg0 = 2 * M_PI * G * b / nn, arg1 = 2 * M_PI * ai * b / nn;
+  double s0, c0, s1, c1;
+  sincos(arg0, &s0, &c0);
+  sincos(arg1, &s1, &c1);
+  const cplx shift0 = make_double2(c0, s0), step = make_double2(c1, s1);
+  const int chunks = g.w2 / g.B2;
+  const unsigned i0 = bk + (unsigned)l;
+  cplx phase = cmul_rn(shift0, cpow_int(step, i0));
+  const cplx stepB = cpow_int(step, (unsigned)g.B2);
+  const unsigned mask = (unsigned)(g.n - 1);
+  unsigned idx = (unsigned)(((unsigned long long)(unsigned)(G % g.n) + (unsigned long long)i0 * (unsigned)ai) & mask);
+  const unsigned idx_step = (unsigned)(((unsigned long long)g.B2 * (unsigned)ai) & mask);
+  const cplx *__restrict__ xs = x + (long long)s * x_stride;
+  double ar = 0.0, aim = 0.0;
+  for (int c = 0; c < chunks; c++) {
+    const cplx v = ldg_stream(xs + idx);
+    const cplx P = cmul_rn(v, phase);
+    const cplx f = __ldg(&taps[(unsigned)c * g.B2 + bk]);
+    ar = __dadd_rn(ar, __dsub_rn(__dmul_rn(f.x, P.x), __dmul_rn(f.y, P.y)));
+    aim = __dadd_rn(aim, __dadd_rn(__dmul_rn(f.y, P.x), __dmul_rn(f.x, P.y)));
+    phase = cmul_rn(phase, stepB);
+    idx = (idx + idx_step) & mask;
+  }
+  samp[(long long)s * g.nslots + g2_base(g) + l * g.B2 + bitrev(bk, g.logB2)] = make_double2(ar, aim);
+}
+
+// ---- the peeling loop ------------------------------------------------------
+constexpr int kPeelThreads = 1024;
+
+struct PeelArgs {
+  const int *draw;
+  cplx *samp;
+  int *head;
+  int *est_key; cplx *est_val;
+  int *t_slot, *t_next; cplx *t_delta;
+  int *hkey, *hidx;
+  int *ans_key; cplx *ans_val;
+  int *count, *rounds;
+  const cplx *fwin1, *fwin2;
+};
+
+struct PeelCtx {
+  V3Geom g;
+  int a, ai, b, shift, off, goff;
+  cplx *samp;
+  int *head;
+  int *est_key; cplx *est_val;
+  int *t_slot, *t_next; cplx *t_delta;
+  int *hkey, *hidx;
+  int *ans_key; cplx *ans_val;
+  const cplx *fwin1, *fwin2;
+};
+
+__device__ __forceinline__ cplx fwin_at(const cplx *__restrict__ fwin, int half, int n, int dist)
+{
+  // filterf[dist] with dist in [0, n): the window holds indices (-half .. +half) mod n
+  const int sd = dist < n / 2 ? dist : dist - n;
+  return __ldg(&fwin[half + sd]);
+}
+
+// C99 complex division as libgcc's __divdc3 evaluates it in the normal range
+// (Smith's method, with its alternate order when the ratio underflows);
+// reference: `median_value / filter_value`, computefourier-3.0.cc:619-620
+__device__ __forceinline__ cplx cdiv_smith(cplx x, cplx y)
+{
+  const double a = x.x, b = x.y, c = y.x, d = y.y;
+  const double RMIN = 2.2250738585072014e-308;
+  double rx, ry;
+  if (fabs(c) < fabs(d)) {
+    const double ratio = __ddiv_rn(c, d);
+    const double denom = __dadd_rn(__dmul_rn(c, ratio), d);
+    if (fabs(ratio) > RMIN) {
+      rx = __ddiv_rn(__dadd_rn(__dmul_rn(a, ratio), b), denom);
+      ry = __ddiv_rn(__dsub_rn(__dmul_rn(b, ratio), a), denom);
+    } else {
+      rx = __ddiv_rn(__dadd_rn(__dmul_rn(c, __ddiv_rn(a, d)), b), denom);
+      ry = __ddiv_rn(__dsub_rn(__dmul_rn(c, __ddiv_rn(b, d)), a), denom);
+    }
+  } else {
+    const double ratio = __ddiv_rn(d, c);
+    const double denom = __dadd_rn(__dmul_rn(d, ratio), c);
+    if (fabs(ratio) > RMIN) {
+      rx = __ddiv_rn(__dadd_rn(__dmul_rn(b, ratio), a), denom);
+      ry = __ddiv_rn(__dsub_rn(b, __dmul_rn(a, ratio)), denom);
+    } else {
+      rx = __ddiv_rn(__dadd_rn(__dmul_rn(d, __ddiv_rn(b, c)), a), denom);
+      ry = __ddiv_rn(__dsub_rn(b, __dmul_rn(d, __ddiv_rn(a, c))), denom);
+    }
+  }
+  return make_double2(rx, ry);
+}
+
+// block-wide ordered append: every thread may contribute one (key, val); returns new total
+__device__ int ordered_append(bool have, int key, cplx val, int base, int *keys, cplx *vals, int cap,
+                              unsigned *warp_tot)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned bal = __ballot_sync(0xffffffffu, have);
+  if (lane == 0) warp_tot[warp] = __popc(bal);
+  __syncthreads();
+  unsigned off = 0, tot = 0;
+  for (int w = 0; w < kPeelThreads / 32; w++) {
+    const unsigned c = warp_tot[w];
+    if (w < warp) off += c;
+    tot += c;
+  }
+  if (have) {
+    const int pos = base + (int)off + __popc(bal & ((1u << lane) - 1u));
+    if (pos < cap) { keys[pos] = key; vals[pos] = val; }
+  }
+  __syncthreads();
+  return base + (int)tot;
+}
+
+// computefourier-3.0.cc:642-776
+__device__ int decode_mansour(const PeelCtx &c, unsigned *warp_tot)
+{
+  const V3Geom &g = c.g;
+  const double PI2 = 2 * M_PI, N_OVER_PI2 = (double)g.n / PI2, PI2_OVER_N = PI2 / (double)g.n;
+  const unsigned FREQ_MASK = ((unsigned)(g.n - 1)) & ~((unsigned)g.W - 1u);
+  const double NORM = 1. / (double)g.W, NORM2 = NORM * NORM;
+  const cplx *p0 = c.samp + man_base(g), *p1 = p0 + g.W;
+  int found = 0;
+  for (int base = 0; base < g.W; base += kPeelThreads) {
+    const int bk = base + threadIdx.x;
+    bool have = false;
+    int key = 0;
+    cplx val = make_double2(0, 0);
+    if (bk < g.W) {
+      const cplx s0 = p0[bk], s1 = p1[bk];
+      const double e0 = __dadd_rn(__dmul_rn(s0.x, s0.x), __dmul_rn(s0.y, s0.y));
+      const double e1 = __dadd_rn(__dmul_rn(s1.x, s1.x), __dmul_rn(s1.y, s1.y));
+      const double zero_check = __dadd_rn(__dmul_rn(e0, NORM2), __dmul_rn(e1, NORM2));
+      if (zero_check > 1e-8) {
+        const double c0 = __dmul_rn(e0, NORM2), c1 = __dmul_rn(e1, NORM2);
+        const double d0 = atan2(s0.y * NORM, s0.x * NORM), d1 = atan2(s1.y * NORM, s1.x * NORM);
+        const double inv = 1. / c0;
+        const double bb = c1 * inv - 1;
+        const double error = bb * bb;
+        if (error < g.n * 1e-10 && c0 > 0.01) {
+          const double slope = d1 - d0;
+          const int freq1 = (int)llrint(slope * N_OVER_PI2);
+          const int freq3 = (int)(((unsigned)freq1 & FREQ_MASK) | (unsigned)bk);
+          const int freq_offset = (int)((unsigned)freq3 * (unsigned)c.off);     // 32-bit wrap, :743
+          const double phase = d0 - PI2_OVER_N * freq_offset;
+          const double mag = sqrt(c0);
+          double sn, cs;
+          sincos(phase, &sn, &cs);
+          have = true;
+          key = freq3;
+          val = make_double2(mag * cs, mag * sn);
+        }
+      }
+    }
+    found = ordered_append(have, key, val, found, c.est_key, c.est_val, g.est_cap, warp_tot);
+  }
+  return found < g.est_cap ? found : g.est_cap;
+}
+
+// computefourier-3.0.cc:484-640
+__device__ int decode_gauss(const PeelCtx &c, int which /*1: first window, 2: permuted*/, unsigned *warp_tot)
+{
+  const V3Geom &g = c.g;
+  const int B = which == 1 ? g.B1 : g.B2;
+  const int a = which == 1 ? 1 : c.a, b = which == 1 ? 0 : c.b;
+  const cplx *fwin = which == 1 ? c.fwin1 : c.fwin2;
+  const int half = which == 1 ? g.fw_half1 : g.fw_half2;
+  const cplx *p0 = c.samp + (which == 1 ? g1_base(g) : g2_base(g)), *p1 = p0 + B;
+  const double PI2 = 2 * M_PI, N_OVER_PI2 = (double)g.n / PI2;
+  const double PI2_A_OFFSET_OVER_N = PI2 * a * c.goff / (double)g.n;
+  const double BUCKETS_OVER_N = (double)B / (double)g.n;
+  const unsigned n1 = (unsigned)(g.n - 1), Bm = (unsigned)(B - 1);
+  const unsigned N_OVER_BUCKETS = (unsigned)(g.n / B);
+  int found = 0;
+  for (int base = 0; base < B; base += kPeelThreads) {
+    const int bk = base + threadIdx.x;
+    bool have = false;
+    int key = 0;
+    cplx val = make_double2(0, 0);
+    if (bk < B) {
+      const cplx s0 = p0[bk], s1 = p1[bk];
+      double c0 = __dadd_rn(__dmul_rn(s0.x, s0.x), __dmul_rn(s0.y, s0.y));
+      const double c1 = __dadd_rn(__dmul_rn(s1.x, s1.x), __dmul_rn(s1.y, s1.y));
+      if (__dadd_rn(c0, c1) > 1e-8) {
+        const double d0 = atan2(s0.y, s0.x), d1 = atan2(s1.y, s1.x);
+        const double error_b = c1 / c0 - 1;
+        double error = error_b * error_b;
+        error /= (double)g.n;
+        if (error < 1e-12 && c0 > 0.01) {
+          const double slope = d1 - d0;
+          int freq = (int)llrint(N_OVER_PI2 * slope) + g.n;
+          freq = (int)((unsigned)freq & n1);
+          const unsigned hashed_to = (unsigned)llrint(freq * BUCKETS_OVER_N) & Bm;
+          if (hashed_to == (unsigned)bk) {
+            const double phase = d0 - PI2_A_OFFSET_OVER_N * freq;
+            c0 = sqrt(c0);
+            double sn, cs;
+            sincos(phase, &sn, &cs);
+            cplx v = make_double2(c0 * cs, c0 * sn);
+            const int dist = (int)((hashed_to * N_OVER_BUCKETS - (unsigned)freq + (unsigned)g.n) & n1);
+            v = cdiv_smith(v, fwin_at(fwin, half, g.n, dist));
+            const unsigned pf = (unsigned)(((unsigned long long)(unsigned)freq * (unsigned)a) & n1);   // timesmod
+            have = true;
+            key = (int)((pf - (unsigned)b + (unsigned)g.n) & n1);
+            val = v;
+          }
+        }
+      }
+    }
+    found = ordered_append(have, key, val, found, c.est_key, c.est_val, g.est_cap, warp_tot);
+  }
+  return found < g.est_cap ? found : g.est_cap;
+}
+
+// the 6 deltas one coefficient leaves in a windowed filter's buckets (:354-463)
+__device__ void gauss_targets(const PeelCtx &c, int which, int key, cplx value, int init_G_offset,
+                              int *slots, cplx *deltas)
+{
+  const V3Geom &g = c.g;
+  const int B = which == 1 ? g.B1 : g.B2;
+  const int base = which == 1 ? g1_base(g) : g2_base(g);
+  const cplx *fwin = which == 1 ? c.fwin1 : c.fwin2;
+  const int half = which == 1 ? g.fw_half1 : g.fw_half2;
+  const int n = g.n, n1 = n - 1;
+  const double PI2_DIV_N = 2 * M_PI / (double)n;
+  const unsigned n_over_B = (unsigned)(n / B);
+  const int h = (int)(key * 1. / n_over_B + 0.5) % B;
+  const int dist1 = (int)(((unsigned)h * n_over_B - (unsigned)key + (unsigned)n) & (unsigned)n1);
+  const int dist2 = (int)(((unsigned)dist1 + (unsigned)n + n_over_B) & (unsigned)n1);
+  const int dist3 = (int)(((unsigned)dist1 + (unsigned)n + (unsigned)n - n_over_B) & (unsigned)n1);
+  const int key_offset = (int)((unsigned)key * (unsigned)init_G_offset) % n;            // :381
+  const int key_offset2 = (int)((unsigned)key * (unsigned)(init_G_offset + 1)) % n;     // :382
+  double a2, b2, a22, b22;
+  sincos(PI2_DIV_N * key_offset, &b2, &a2);
+  sincos(PI2_DIV_N * key_offset2, &b22, &a22);
+  const cplx v1 = make_double2(value.x * a2 - value.y * b2, value.x * b2 + value.y * a2);
+  const cplx v2 = make_double2(value.x * a22 - value.y * b22, value.x * b22 + value.y * a22);
+  const cplx f1 = fwin_at(fwin, half, n, dist1), f2 = fwin_at(fwin, half, n, dist2),
+             f3 = fwin_at(fwin, half, n, dist3);
+  const int hp = (h + 1) % B, hm = (h + B - 1) % B;
+  slots[0] = base + h;      deltas[0] = cmul_rn(v1, f1);
+  slots[1] = base + hp;     deltas[1] = cmul_rn(v1, f2);
+  slots[2] = base + hm;     deltas[2] = cmul_rn(v1, f3);
+  slots[3] = base + B + h;  deltas[3] = cmul_rn(v2, f1);
+  slots[4] = base + B + hp; deltas[4] = cmul_rn(v2, f2);
+  slots[5] = base + B + hm; deltas[5] = cmul_rn(v2, f3);
+}
+
+// :300-351
+__device__ void mansour_targets(const PeelCtx &c, int key, cplx value, int *slots, cplx *deltas)
+{
+  const V3Geom &g = c.g;
+  const double PI2_OVER_N = 2 * M_PI / (double)g.n;
+  const int h = key & (g.W - 1);
+  double s0, c0, s1, c1;
+  sincos(PI2_OVER_N * key * c.off, &s0, &c0);
+  sincos(PI2_OVER_N * key * (c.off + 1), &s1, &c1);
+  const double W = (double)g.W;
+  slots[0] = man_base(g) + h;
+  deltas[0] = make_double2(W * (value.x * c0 - value.y * s0), W * (value.x * s0 + value.y * c0));
+  slots[1] = man_base(g) + g.W + h;
+  deltas[1] = make_double2(W * (value.x * c1 - value.y * s1), W * (value.x * s1 + value.y * c1));
+}
+
+// Subtract, from every touched bucket, the deltas of items [0, F) in item order.
+// keys/vals: the items; which groups to peel is given by the flags.
+// key_is_ans: keys are plain frequencies (UPDATE_ALL semantics); the permuted filter sees
+// (key*ai + shift) mod n   (:465-482, :944)
+__device__ void peel_apply(const PeelCtx &c, const int *keys, const cplx *vals, int F, bool do_g2,
+                           bool do_g1, bool do_man)
+{
+  const V3Geom &g = c.g;
+  for (int i = threadIdx.x; i < F; i += kPeelThreads) {
+    const int key = keys[i];
+    const cplx v = vals[i];
+    int slots[14];
+    cplx deltas[14];
+#pragma unroll
+    for (int q = 0; q < 14; q++) slots[q] = -1;
+    if (do_g2) {
+      const int key2 = (int)(((((unsigned long long)(unsigned)key * (unsigned)c.ai) & (unsigned)(g.n - 1)) +
+                              (unsigned)c.shift) % (unsigned)g.n);
+      const int a_off = (int)((unsigned)c.a * (unsigned)c.goff);
+      gauss_targets(c, 2, key2, v, a_off, slots, deltas);
+    }
+    if (do_g1) gauss_targets(c, 1, key, v, c.goff, slots + 6, deltas + 6);
+    if (do_man) mansour_targets(c, key, v, slots + 12, deltas + 12);
+#pragma unroll
+    for (int q = 0; q < 14; q++) {
+      const int t = i * 14 + q;
+      c.t_slot[t] = slots[q];
+      if (slots[q] >= 0) {
+        c.t_delta[t] = deltas[q];
+        c.t_next[t] = atomicExch(&c.head[slots[q]], t);
+      }
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < F * 14; t += kPeelThreads) {
+    const int slot = c.t_slot[t];
+    if (slot < 0 || c.head[slot] != t) continue;      // one leader per touched bucket
+    cplx val = c.samp[slot];
+    int last = -1;
+    for (;;) {                                         // ascending target id == item order
+      int best = 0x7fffffff;
+      for (int id = t; id >= 0; id = c.t_next[id])
+        if (id > last && id < best) best = id;
+      if (best == 0x7fffffff) break;
+      val = csub_rn(val, c.t_delta[best]);
+      last = best;
+    }
+    c.samp[slot] = val;
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < F * 14; t += kPeelThreads) {
+    const int slot = c.t_slot[t];
+    if (slot >= 0) c.head[slot] = -1;
+  }
+  __syncthreads();
+}
+
+__device__ __forceinline__ unsigned hash_key(int key, int log_hash)
+{
+  return ((unsigned)key * 2654435761u) >> (32 - log_hash);
+}
+
+__device__ int hash_find(const PeelCtx &c, int key)
+{
+  const unsigned m = (unsigned)c.g.hash_size - 1u;
+  for (unsigned h = hash_key(key, c.g.log_hash);; h = (h + 1) & m) {
+    const int k = c.hkey[h];
+    if (k == key) return c.hidx[h];
+    if (k == -1) return -1;
+  }
+}
+
+__device__ void hash_insert(const PeelCtx &c, int key, int idx)
+{
+  const unsigned m = (unsigned)c.g.hash_size - 1u;
+  for (unsigned h = hash_key(key, c.g.log_hash);; h = (h + 1) & m) {
+    const int prev = atomicCAS(&c.hkey[h], -1, key);
+    if (prev == -1 || prev == key) { c.hidx[h] = idx; return; }
+  }
+}
+
+// ans[key] (+)= val for the F decoded items, new keys appended in item order
+// (:850, :909-913, :969-973, :1025-1029)
+__device__ int ans_accumulate(const PeelCtx &c, int F, int ans_count, bool assign, unsigned *warp_tot,
+                              int *scratch_idx)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int base = 0; base < F; base += kPeelThreads) {
+    const int i = base + threadIdx.x;
+    const bool have = i < F;
+    int idx = -1;
+    if (have) idx = hash_find(c, c.est_key[i]);
+    const bool is_new = have && idx < 0;
+    const unsigned bal = __ballot_sync(0xffffffffu, is_new);
+    if (lane == 0) warp_tot[warp] = __popc(bal);
+    __syncthreads();
+    unsigned off = 0, tot = 0;
+    for (int w = 0; w < kPeelThreads / 32; w++) {
+      const unsigned cc = warp_tot[w];
+      if (w < warp) off += cc;
+      tot += cc;
+    }
+    if (is_new) {
+      idx = ans_count + (int)off + __popc(bal & ((1u << lane) - 1u));
+      if (idx < c.g.ans_cap) {
+        c.ans_key[idx] = c.est_key[i];
+        c.ans_val[idx] = make_double2(0.0, 0.0);
+        hash_insert(c, c.est_key[i], idx);
+      }
+    }
+    if (have && idx >= 0 && idx < c.g.ans_cap) {
+      const cplx v = c.est_val[i];
+      c.ans_val[idx] = assign ? v : cadd_rn(c.ans_val[idx], v);
+    }
+    (void)scratch_idx;
+    ans_count += (int)tot;
+    if (ans_count > c.g.ans_cap) ans_count = c.g.ans_cap;
+    __syncthreads();
+  }
+  return ans_count;
+}
+
+__device__ int block_count(bool flag, unsigned *warp_tot)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const unsigned bal = __ballot_sync(0xffffffffu, flag);
+  if (lane == 0) warp_tot[warp] = __popc(bal);
+  __syncthreads();
+  int tot = 0;
+  for (int w = 0; w < kPeelThreads / 32; w++) tot += (int)warp_tot[w];
+  __syncthreads();
+  return tot;
+}
+
+__global__ void __launch_bounds__(kPeelThreads)
+v3_peel_kernel(V3Geom g, PeelArgs a)
+{
+  __shared__ unsigned warp_tot[32];
+  const int s = blockIdx.x;
+  PeelCtx c;
+  c.g = g;
+  const int *d = a.draw + s * D_INTS;
+  c.a = d[D_A]; c.ai = d[D_AI]; c.b = d[D_B]; c.shift = d[D_SHIFT]; c.off = d[D_OFF]; c.goff = d[D_GOFF];
+  c.samp = a.samp + (long long)s * g.nslots;
+  c.head = a.head + (long long)s * g.nslots;
+  c.est_key = a.est_key + (long long)s * g.est_cap;
+  c.est_val = a.est_val + (long long)s * g.est_cap;
+  c.t_slot = a.t_slot + (long long)s * g.tgt_cap * 14;
+  c.t_next = a.t_next + (long long)s * g.tgt_cap * 14;
+  c.t_delta = a.t_delta + (long long)s * g.tgt_cap * 14;
+  c.hkey = a.hkey + (long long)s * g.hash_size;
+  c.hidx = a.hidx + (long long)s * g.hash_size;
+  c.ans_key = a.ans_key + (long long)s * g.ans_cap;
+  c.ans_val = a.ans_val + (long long)s * g.ans_cap;
+  c.fwin1 = a.fwin1; c.fwin2 = a.fwin2;
+
+  for (long long i = threadIdx.x; i < g.nslots; i += kPeelThreads) c.head[i] = -1;
+  for (int i = threadIdx.x; i < g.hash_size; i += kPeelThreads) c.hkey[i] = -1;
+  __syncthreads();
+
+  int ans_count = 0;
+  // ---- aliasing filter: decode, record, clear the decoded buckets (:842-855) ----
+  int F = decode_mansour(c, warp_tot);
+  ans_count = ans_accumulate(c, F, ans_count, true, warp_tot, nullptr);
+  for (int i = threadIdx.x; i < F; i += kPeelThreads) {
+    // MAN_SAMP[j + 2*(f % W)] = 0 for j = 0,1: in the interleaved layout that is
+    // (bucket f % W, shift 0) and (bucket f % W, shift 1)
+    const int h = c.est_key[i] & (g.W - 1);
+    c.samp[man_base(g) + h] = make_double2(0.0, 0.0);
+    c.samp[man_base(g) + g.W + h] = make_double2(0.0, 0.0);
+  }
+  __syncthreads();
+  if (F == g.k) {
+    // :859-860: the reference returns here BEFORE copying its map to the output
+    if (threadIdx.x == 0) { a.count[s] = 0; a.rounds[s] = 0; }
+    return;
+  }
+  // ---- first window: peel what is known, decode, peel from window 1 + aliasing (:881-924) ----
+  peel_apply(c, c.ans_key, c.ans_val, ans_count, false, true, false);
+  F = decode_gauss(c, 1, warp_tot);
+  ans_count = ans_accumulate(c, F, ans_count, false, warp_tot, nullptr);
+  peel_apply(c, c.est_key, c.est_val, F, false, true, true);
+  // ---- permuted window (:940-981) ----
+  peel_apply(c, c.ans_key, c.ans_val, ans_count, true, false, false);
+  F = decode_gauss(c, 2, warp_tot);
+  ans_count = ans_accumulate(c, F, ans_count, false, warp_tot, nullptr);
+  peel_apply(c, c.est_key, c.est_val, F, true, true, true);
+  // ---- round robin until the occupied-bucket counts repeat (:991-1076) ----
+  int prev_m = 0, prev_1 = 0, prev_2 = 0, rounds = 0;
+  for (int nana = 0;; nana++) {
+    if (nana % 3 == 0) F = decode_mansour(c, warp_tot);
+    else F = decode_gauss(c, nana % 3 == 1 ? 1 : 2, warp_tot);
+    ans_count = ans_accumulate(c, F, ans_count, false, warp_tot, nullptr);
+    peel_apply(c, c.est_key, c.est_val, F, true, true, true);
+    rounds = nana + 1;
+    if (nana % 3 == 2) {
+      int cm = 0, c1 = 0, c2 = 0;
+      // the reference indexes its interleaved arrays with a plain j < B (:1047-1057):
+      // entry j is (bucket j/2, shift j%2)
+      for (int base = 0; base < g.B1; base += kPeelThreads) {
+        const int j = base + threadIdx.x;
+        bool f = false;
+        if (j < g.B1) { const cplx v = c.samp[g1_base(g) + (j & 1) * g.B1 + (j >> 1)]; f = cabs2_rn(v) > 1e-6; }
+        c1 += block_count(f, warp_tot);
+      }
+      for (int base = 0; base < g.B2; base += kPeelThreads) {
+        const int j = base + threadIdx.x;
+        bool f = false;
+        if (j < g.B2) { const cplx v = c.samp[g2_base(g) + (j & 1) * g.B2 + (j >> 1)]; f = cabs2_rn(v) > 1e-6; }
+        c2 += block_count(f, warp_tot);
+      }
+      for (int base = 0; base < g.W; base += kPeelThreads) {
+        const int j = base + threadIdx.x;
+        bool f = false;
+        if (j < g.W) {
+          const cplx v = c.samp[man_base(g) + j];
+          const double r = v.x / (double)g.W, m = v.y / (double)g.W;
+          f = __dadd_rn(__dmul_rn(r, r), __dmul_rn(m, m)) > 1e-6;
+        }
+        cm += block_count(f, warp_tot);
+      }
+      if (prev_m == cm && prev_1 == c1 && prev_2 == c2) break;
+      prev_m = cm; prev_1 = c1; prev_2 = c2;
+      if (nana > 3000) break;      // safety net; the reference has none
+    }
+  }
+  if (threadIdx.x == 0) { a.count[s] = ans_count; a.rounds[s] = rounds; }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------
+static int floor_to_pow2_v3(double x)
+{
+  unsigned int ans;
+  for (ans = 1; ans <= x; ans <<= 1) {}
+  return (int)(ans / 2);
+}
+
+static V3Geom make_geom(const PlanImpl *p)
+{
+  const PlanV3 &v = *p->v3;
+  V3Geom g;
+  g.n = p->n; g.logn = p->logn; g.k = p->k;
+  g.W = v.W_Man; g.logW = v.logW; g.B1 = v.B_g1; g.logB1 = v.logB1; g.B2 = v.B_g2; g.logB2 = v.logB2;
+  g.w1 = v.filt[0].w; g.w2 = v.filt[1].w;
+  g.fw_half1 = v.filt[0].fw_half; g.fw_half2 = v.filt[1].fw_half;
+  g.nslots = v.nslots;
+  g.est_cap = v.est_cap; g.ans_cap = v.ans_cap; g.tgt_cap = v.tgt_cap; g.hash_size = v.hash_size; g.log_hash = v.log_hash;
+  return g;
+}
+
+static void v3_free_scratch(PlanV3 &v)
+{
+  cudaFree(v.d_samp); cudaFree(v.d_head); cudaFree(v.d_est_key); cudaFree(v.d_est_val);
+  cudaFree(v.d_t_slot); cudaFree(v.d_t_next); cudaFree(v.d_t_delta); cudaFree(v.d_hkey);
+  cudaFree(v.d_hidx); cudaFree(v.d_ans_key); cudaFree(v.d_ans_val); cudaFree(v.d_count);
+  cudaFree(v.d_rounds); cudaFree(v.d_draw);
+  for (int i = 0; i < kStageSlots; i++) {
+    if (v.h_draw[i]) cudaFreeHost(v.h_draw[i]);
+    v.h_draw[i] = nullptr;
+  }
+  v.d_samp = nullptr; v.d_head = nullptr; v.d_est_key = nullptr; v.d_est_val = nullptr;
+  v.d_t_slot = nullptr; v.d_t_next = nullptr; v.d_t_delta = nullptr; v.d_hkey = nullptr;
+  v.d_hidx = nullptr; v.d_ans_key = nullptr; v.d_ans_val = nullptr; v.d_count = nullptr;
+  v.d_rounds = nullptr; v.d_draw = nullptr;
+  v.cap = 0;
+}
+
+static int v3_ensure_capacity(PlanImpl *p, int nsig)
+{
+  PlanV3 &v = *p->v3;
+  if (nsig <= v.cap) return 0;
+  SFFTB_CUDA(cudaStreamSynchronize(p->stream));
+  v3_free_scratch(v);
+  const long long S = nsig;
+  SFFTB_CUDA(cudaMalloc(&v.d_samp, sizeof(cplx) * S * v.nslots));
+  SFFTB_CUDA(cudaMalloc(&v.d_head, sizeof(int) * S * v.nslots));
+  SFFTB_CUDA(cudaMalloc(&v.d_est_key, sizeof(int) * S * v.est_cap));
+  SFFTB_CUDA(cudaMalloc(&v.d_est_val, sizeof(cplx) * S * v.est_cap));
+  SFFTB_CUDA(cudaMalloc(&v.d_t_slot, sizeof(int) * S * v.tgt_cap * 14));
+  SFFTB_CUDA(cudaMalloc(&v.d_t_next, sizeof(int) * S * v.tgt_cap * 14));
+  SFFTB_CUDA(cudaMalloc(&v.d_t_delta, sizeof(cplx) * S * v.tgt_cap * 14));
+  SFFTB_CUDA(cudaMalloc(&v.d_hkey, sizeof(int) * S * v.hash_size));
+  SFFTB_CUDA(cudaMalloc(&v.d_hidx, sizeof(int) * S * v.hash_size));
+  SFFTB_CUDA(cudaMalloc(&v.d_ans_key, sizeof(int) * S * v.ans_cap));
+  SFFTB_CUDA(cudaMalloc(&v.d_ans_val, sizeof(cplx) * S * v.ans_cap));
+  SFFTB_CUDA(cudaMalloc(&v.d_count, sizeof(int) * S));
+  SFFTB_CUDA(cudaMalloc(&v.d_rounds, sizeof(int) * S));
+  SFFTB_CUDA(cudaMalloc(&v.d_draw, sizeof(int) * S * D_INTS));
+  for (int i = 0; i < kStageSlots; i++)
+    SFFTB_CUDA(cudaHostAlloc(&v.h_draw[i], sizeof(int) * S * D_INTS, cudaHostAllocDefault));
+  v.cap = nsig;
+  return 0;
+}
+
+int v3_build(PlanImpl *p, int n_req, int k)
+{
+  // src/sfft.cc:506-579
+  const unsigned n = (unsigned)floor_to_pow2_v3(n_req);
+  if ((int)n != n_req || n < 16) {
+    set_error("sfft_make_plan: n must be a power of two >= 16");
+    return -1;
+  }
+  if (k < 8) { set_error("sfft_make_plan(v3): k must be >= 8"); return -1; }
+  p->v3 = new PlanV3();
+  PlanV3 &v = *p->v3;
+  p->n = (int)n; p->logn = ilog2(n); p->k = k;
+  v.W_Man = floor_to_pow2_v3(10.0 * (double)k);
+  if ((unsigned)v.W_Man > n / 2) v.W_Man = (int)(n / 2);
+  const double BB = (unsigned)(1.0 * (double)k);
+  v.B_g1 = floor_to_pow2_v3(BB);
+  const int b_g1 = (int)(1.00 * ((double)n / v.B_g1));
+  const double BB2 = (unsigned)(0.25 * (double)k);
+  v.B_g2 = floor_to_pow2_v3(BB2);
+  const int b_g2 = (int)(1.00 * ((double)n / v.B_g2));
+  if (v.B_g1 < 4 || v.B_g2 < 4 || (unsigned)v.B_g1 > n || (unsigned)v.W_Man < 2) {
+    set_error("sfft_make_plan(v3): bucket counts out of range for this (n, k)");
+    return -1;
+  }
+  v.logW = ilog2((unsigned)v.W_Man); v.logB1 = ilog2((unsigned)v.B_g1); v.logB2 = ilog2((unsigned)v.B_g2);
+  // response entries read: +-n/2B around 0 and the same one bucket up/down (:375-379, :612-616)
+  const int half1 = 3 * (int)(n / v.B_g1) / 2 + 2, half2 = 3 * (int)(n / v.B_g2) / 2 + 2;
+  const int cap1 = (int)n / 2 - 1;
+  if (build_filter(p->logn, 0.5 / BB, 1.e-8, b_g1, half1 < cap1 ? half1 : cap1, &v.filt[0], p->stream)) return -1;
+  if (build_filter(p->logn, 0.5 / BB2, 1.e-8, b_g2, half2 < cap1 ? half2 : cap1, &v.filt[1], p->stream)) return -1;
+  if (v.filt[0].w / v.B_g1 < 1 || v.filt[1].w / v.B_g2 < 1 || v.filt[1].w + 2 >= (int)n) {
+    set_error("sfft_make_plan(v3): window shorter than one bucket sweep (reference asserts, cf3.cc:221)");
+    return -1;
+  }
+  int twN = v.W_Man;
+  if (v.B_g1 > twN) twN = v.B_g1;
+  if (v.B_g2 > twN) twN = v.B_g2;
+  v.log_twN = ilog2((unsigned)twN);
+  std::vector<cplx> tw((size_t)(twN > 1 ? twN - 1 : 1));
+  host_twiddle_levels(twN, tw.data());
+  SFFTB_CUDA(cudaMalloc(&v.d_tw, sizeof(cplx) * tw.size()));
+  SFFTB_CUDA(cudaMemcpyAsync(v.d_tw, tw.data(), sizeof(cplx) * tw.size(), cudaMemcpyHostToDevice, p->stream));
+  SFFTB_CUDA(cudaStreamSynchronize(p->stream));
+  v.nslots = 2ll * v.B_g2 + 2ll * v.B_g1 + 2ll * v.W_Man;
+  int cap = v.W_Man;
+  if (v.B_g1 > cap) cap = v.B_g1;
+  v.est_cap = cap;
+  v.ans_cap = 8 * k + 2 * v.W_Man;
+  v.tgt_cap = v.ans_cap > v.est_cap ? v.ans_cap : v.est_cap;
+  v.hash_size = 1;
+  v.log_hash = 0;
+  while (v.hash_size < 4 * v.ans_cap) { v.hash_size <<= 1; v.log_hash++; }
+  for (int i = 0; i < kStageSlots; i++) SFFTB_CUDA(cudaEventCreateWithFlags(&v.ev[i], cudaEventDisableTiming));
+  return v3_ensure_capacity(p, 1);
+}
+
+void v3_free(PlanImpl *p)
+{
+  if (!p->v3) return;
+  PlanV3 &v = *p->v3;
+  v3_free_scratch(v);
+  free_filter(&v.filt[0]);
+  free_filter(&v.filt[1]);
+  cudaFree(v.d_tw);
+  for (int i = 0; i < kStageSlots; i++)
+    if (v.ev[i]) cudaEventDestroy(v.ev[i]);
+  delete p->v3;
+  p->v3 = nullptr;
+}
+
+// src/computefourier-3.0.cc:800-810: random() until odd, one more random(), two drand48()
+int v3_draw(const PlanImpl *p, sfftb_draw *d)
+{
+  const int n = p->n;
+  int a = 0;
+  while (gcd_pub(a, n) != 1) a = (int)(random() % n);
+  d->v3_a = a;
+  d->v3_ai = mod_inverse_pub(a, n);
+  d->v3_b = (int)(random() % n);
+  d->v3_init_offset = (int)(unsigned)floor(drand48() * n);
+  d->v3_init_G_offset = (int)(unsigned)floor(drand48() * n);
+  return 0;
+}
+
+int v3_exec(PlanImpl *p, const cplx *d_in, long long stride, int nsig, const sfftb_draw *draws)
+{
+  PlanV3 &v = *p->v3;
+  cudaStream_t st = p->stream;
+  if (v3_ensure_capacity(p, nsig)) return -1;
+  timer_begin(p);
+  const V3Geom g = make_geom(p);
+  const int slot = v.next_slot;
+  v.next_slot = (v.next_slot + 1) % kStageSlots;
+  SFFTB_CUDA(cudaEventSynchronize(v.ev[slot]));
+  int *h = v.h_draw[slot];
+  for (int s = 0; s < nsig; s++) {
+    const sfftb_draw &d = draws[s];
+    int *o = h + s * D_INTS;
+    o[D_A] = d.v3_a; o[D_AI] = d.v3_ai; o[D_B] = d.v3_b;
+    o[D_SHIFT] = ((int)((unsigned)d.v3_ai * (unsigned)d.v3_b) % p->n + p->n) % p->n;   // :807, 32-bit wrap
+    o[D_OFF] = d.v3_init_offset; o[D_GOFF] = d.v3_init_G_offset;
+    o[6] = 0; o[7] = 0;
+  }
+  SFFTB_CUDA(cudaMemcpyAsync(v.d_draw, h, sizeof(int) * (long long)nsig * D_INTS, cudaMemcpyHostToDevice, st));
+  SFFTB_CUDA(cudaEventRecord(v.ev[slot], st));
+  timer_mark(p, "stage_draws");
+
+  {
+    dim3 grid((unsigned)ceil_div(g.W, 256), 2, (unsigned)nsig);
+    v3_mansour_kernel<<<grid, 256, 0, st>>>(g, d_in, stride, v.d_draw, v.d_samp);
+    SFFTB_LAUNCH_CHECK();
+    dim3 grid1((unsigned)ceil_div(g.B1, 128), 2, (unsigned)nsig);
+    v3_gauss_kernel<<<grid1, 128, 0, st>>>(g, d_in, stride, v.d_draw, v.filt[0].time, v.d_samp);
+    SFFTB_LAUNCH_CHECK();
+    dim3 grid2((unsigned)ceil_div(g.B2, 64), 2, (unsigned)nsig);
+    v3_gauss_perm_kernel<<<grid2, 64, 0, st>>>(g, d_in, stride, v.d_draw, v.filt[1].time, v.d_samp);
+    SFFTB_LAUNCH_CHECK();
+  }
+  timer_mark(p, "bucketise");
+  if (fft_dit_inplace(v.d_samp + 0, g.logB2, 2, g.B2, nsig, g.nslots, v.d_tw, v.log_twN, -1, st)) return -1;
+  if (fft_dit_inplace(v.d_samp + 2 * g.B2, g.logB1, 2, g.B1, nsig, g.nslots, v.d_tw, v.log_twN, -1, st)) return -1;
+  if (fft_dit_inplace(v.d_samp + 2 * g.B2 + 2 * g.B1, g.logW, 2, g.W, nsig, g.nslots, v.d_tw, v.log_twN, -1, st)) return -1;
+  timer_mark(p, "bucket_fft");
+
+  PeelArgs a;
+  a.draw = v.d_draw; a.samp = v.d_samp; a.head = v.d_head;
+  a.est_key = v.d_est_key; a.est_val = v.d_est_val;
+  a.t_slot = v.d_t_slot; a.t_next = v.d_t_next; a.t_delta = v.d_t_delta;
+  a.hkey = v.d_hkey; a.hidx = v.d_hidx; a.ans_key = v.d_ans_key; a.ans_val = v.d_ans_val;
+  a.count = v.d_count; a.rounds = v.d_rounds;
+  a.fwin1 = v.filt[0].fwin; a.fwin2 = v.filt[1].fwin;
+  v3_peel_kernel<<<nsig, kPeelThreads, 0, st>>>(g, a);
+  SFFTB_LAUNCH_CHECK();
+  timer_mark(p, "peel");
+  p->last_nsig = nsig;
+  return 0;
+}
+
+int v3_info(const PlanImpl *p, sfftb_info *info)
+{
+  const PlanV3 &v = *p->v3;
+  info->B_g1 = v.B_g1; info->w_g1 = v.filt[0].w; info->B_g2 = v.B_g2; info->w_g2 = v.filt[1].w;
+  info->W_Man = v.W_Man;
+  info->max_hits = v.ans_cap;
+  info->gather_samples = 2ll * v.W_Man + (long long)(v.filt[0].w / v.B_g1) * v.B_g1 + 1 +
+                         (long long)(v.filt[1].w / v.B_g2) * v.B_g2 + 1;
+  info->gather_tap_bytes = 16ll * (v.filt[0].w + v.filt[1].w);
+  return 0;
+}
+
+int v3_result(PlanImpl *p, const int **loc, const cplx **val, const int **count, long long *cap)
+{
+  PlanV3 &v = *p->v3;
+  *loc = v.d_ans_key; *val = v.d_ans_val; *count = v.d_count; *cap = v.ans_cap;
+  return 0;
+}
+
+int v3_filter_sizes(const PlanImpl *p, int which, int *w, int *fw_len)
+{
+  const PlanV3 &v = *p->v3;
+  if (w) *w = v.filt[which].w;
+  if (fw_len) *fw_len = 2 * v.filt[which].fw_half + 1;
+  return 0;
+}
+
+DeviceFilter *v3_filter(PlanImpl *p, int which) { return &p->v3->filt[which]; }
+
+long long v3_debug_fetch(PlanImpl *p, const char *what, void *dst, size_t capacity)
+{
+  PlanV3 &v = *p->v3;
+  const std::string w(what);
+  const void *src = nullptr;
+  long long bytes = 0;
+  if (w == "gauss_perm_samp") { src = v.d_samp; bytes = sizeof(cplx) * 2ll * v.B_g2; }
+  else if (w == "gauss_samp") { src = v.d_samp + 2 * v.B_g2; bytes = sizeof(cplx) * 2ll * v.B_g1; }
+  else if (w == "man_samp") { src = v.d_samp + 2 * v.B_g2 + 2 * v.B_g1; bytes = sizeof(cplx) * 2ll * v.W_Man; }
+  else if (w == "rounds") { src = v.d_rounds; bytes = sizeof(int); }
+  else if (w == "twiddle") { src = v.d_tw; bytes = sizeof(cplx) * ((1ll << v.log_twN) - 1); }
+  else { set_error("sfftb_debug_fetch: unknown v3 array name"); return -1; }
+  if (bytes > (long long)capacity) { set_error("sfftb_debug_fetch: destination too small"); return -1; }
+  if (cudaMemcpy(dst, src, (size_t)bytes, cudaMemcpyDeviceToHost) != cudaSuccess) {
+    set_error("sfftb_debug_fetch: copy failed");
+    return -1;
+  }
+  return bytes;
+}
 
 }  // namespace sfftb

@@ -73,3 +73,22 @@ def test_integer_helpers(oracle_mod):
 
 def test_oracle_rejects_unknown_version(oracle_mod):
     assert not oracle_mod.lib().orc_make_plan(16384, 50, 7)
+
+
+@pytest.mark.parametrize("n,k", [(16384, 50), (262144, 100)])
+def test_oracle_matches_reference_golden_v3(oracle_mod, n, k):
+    g = load_golden(3, n, k)
+    x, xf = oracle_mod.generate_input(n, k, int(g["srand48_input"]))
+    assert sha(x) == str(g["sha_x"])
+    p = oracle_mod.Plan(n, k, 3)
+    for key in ("B_g1", "w_g1", "B_g2", "w_g2", "W_Man"):
+        assert int(g["param_" + key]) == getattr(p, key), key
+    for nm in ("filtert1", "filterf1", "filtert2", "filterf2"):
+        assert sha(p.arr(nm)) == str(g["sha_" + nm]), nm
+    oracle_mod.seed(int(g["srand"]), int(g["srand48_exec"]))
+    out = p.exec(x)
+    loc = np.flatnonzero(out).astype(np.int32)
+    assert np.array_equal(loc, g["loc"])
+    assert bits_equal(out[loc], g["val"])
+    assert sha(out) == str(g["sha_out"])
+    p.free()

@@ -72,3 +72,36 @@ def test_noisy_input_bit_identical(oracle_mod, ref_mod):
     assert bits_equal(ro, oo)
     rp.free()
     op.free()
+
+
+_V3_CHILD = r"""
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np
+from oracle import ref, oracle
+n, k, s48, sx = (int(a) for a in sys.argv[2:6])
+x, xf = ref.generate_input(n, k, s48)
+rp = ref.RefPlan(n, k, 3)
+op = oracle.Plan(n, k, 3)
+eq = lambda a, b: a.shape == b.shape and a.tobytes() == b.tobytes()
+ok = all(eq(rp.v3_filter(i), op.arr(nm)) for i, nm in enumerate(("filtert1", "filterf1", "filtert2", "filterf2")))
+rp.seed(17, sx); ro = rp.exec(x)
+oracle.seed(17, sx); oo = op.exec(x)
+ok = ok and all(eq(rp.v3_samples(i), op.arr(nm)) for i, nm in enumerate(("man_samp", "gauss_samp", "gauss_perm_samp")))
+ok = ok and eq(ro, oo)
+print("V3_BITEXACT" if ok else "V3_MISMATCH", np.count_nonzero(ro), flush=True)
+os._exit(0)   # the reference has overrun perm_x by now (computefourier-3.0.cc:235 vs sfft.cc:497); skip teardown
+"""
+
+
+@pytest.mark.parametrize("n,k,s48,sx", [(16384, 50, 12345, 999), (65536, 64, 5, 9), (262144, 100, 77, 3),
+                                        (1048576, 500, 11, 4)])
+def test_v3_restatement_bit_identical_to_reference(oracle_mod, ref_mod, n, k, s48, sx):
+    """One reference exec per subprocess: the reference's v3 path writes one element past
+    perm_x and corrupts its heap, so a long-lived process cannot host several execs."""
+    import subprocess
+    import sys
+    from util import ROOT
+    out = subprocess.run([sys.executable, "-c", _V3_CHILD, ROOT, str(n), str(k), str(s48), str(sx)],
+                         capture_output=True, text=True, timeout=600)
+    assert "V3_BITEXACT" in out.stdout, out.stdout + out.stderr
