@@ -161,19 +161,28 @@ int sfftb_densify(sfft_plan *plan, int which, void *d_out);
 long long sfftb_fetch_result(sfft_plan *plan, int which, int *loc, sfft_complex *val,
                              long long capacity);
 
-/* ---- multi-GPU loop sharding (one process per GPU; the exchange itself is
- * done by the caller, e.g. torch.distributed all_gather over NCCL) ----------
- * Phase 1: bucketise + FFT + select for the loops this rank owns
- *          (loop j is owned by rank j % world); leaves the selected-bucket
- *          lists of the owned location loops in d_J.
- * Phase 2: given the J lists of ALL location loops, vote -> hit list, then the
- *          per-loop estimates of this rank's loops for every hit in d_est.
- * Phase 3: given every rank's estimates, take the medians. */
-int sfftb_shard_phase1(sfft_plan *plan, const void *d_in, const sfftb_draw *draw,
-                       int rank, int world, int **d_J, long long *J_elems);
-int sfftb_shard_phase2(sfft_plan *plan, int rank, int world, long long *hits,
-                       double **d_est_re, double **d_est_im);
-int sfftb_shard_phase3(sfft_plan *plan, sfftb_result *result, int sync);
+/* ---- multi-GPU sharding of ONE v1/v2 transform (one process per GPU) --------
+ * The signal is resident on every GPU.  Rank r of `world` bucketises only its own
+ * block of loops (gather + bucket FFT, the bandwidth-heavy part); ONE collective
+ * then makes the bucket spectra complete everywhere -- the caller sums the buffer
+ * returned by sfftb_shard_spectra() over ranks (rows a rank does not own are
+ * zero, so the sum is exact), e.g. torch.distributed.all_reduce over NCCL/NVLink.
+ * Selection and voting are then replicated (they are cheap and deterministic);
+ * estimation covers every hit (v1) or this rank's slice of the pre-filled list
+ * (v2, where that list is the bulk of the work).
+ *
+ *   sfftb_shard_bucketize(plan, d_in, draw, rank, world);
+ *   sfftb_shard_spectra(plan, &ptr, &count);  all_reduce(ptr, count doubles, SUM);
+ *   sfftb_shard_finish(plan, rank, world, &result, sync);
+ *
+ * `draw` must be the same on every rank (draw on rank 0 and broadcast, or seed
+ * libc identically).  v3 has no loop structure to shard: replicas only. */
+int sfftb_shard_bucketize(sfft_plan *plan, const void *d_in, const sfftb_draw *draw, int rank,
+                          int world);
+int sfftb_shard_spectra(sfft_plan *plan, void **d_spectra, long long *n_doubles);
+int sfftb_shard_finish(sfft_plan *plan, int rank, int world, sfftb_result *result, int sync);
+/* loops [begin, end) of the plan's `loops` that `rank` owns (block partition) */
+int sfftb_shard_loops(const sfft_plan *plan, int rank, int world, int *begin, int *end);
 
 /* ---- plan-builder hooks (parity injection / plan cache) ------------------ */
 /* which: 0 = location filter, 1 = estimation filter (v1/v2); 0/1 = first/second

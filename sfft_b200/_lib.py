@@ -70,9 +70,10 @@ SYMBOLS = {
                                      C.POINTER(_ll), _ci]),
     "sfftb_densify": (_ci, [_PP, _ci, _vp]),
     "sfftb_fetch_result": (_ll, [_PP, _ci, _vp, _vp, _ll]),
-    "sfftb_shard_phase1": (_ci, [_PP, _vp, C.POINTER(Draw), _ci, _ci, C.POINTER(_vp), C.POINTER(_ll)]),
-    "sfftb_shard_phase2": (_ci, [_PP, _ci, _ci, C.POINTER(_ll), C.POINTER(_vp), C.POINTER(_vp)]),
-    "sfftb_shard_phase3": (_ci, [_PP, C.POINTER(Result), _ci]),
+    "sfftb_shard_bucketize": (_ci, [_PP, _vp, C.POINTER(Draw), _ci, _ci]),
+    "sfftb_shard_spectra": (_ci, [_PP, C.POINTER(_vp), C.POINTER(_ll)]),
+    "sfftb_shard_finish": (_ci, [_PP, _ci, _ci, C.POINTER(Result), _ci]),
+    "sfftb_shard_loops": (_ci, [_PP, _ci, _ci, C.POINTER(_ci), C.POINTER(_ci)]),
     "sfftb_filter_sizes": (_ci, [_PP, _ci, C.POINTER(_ci), C.POINTER(_ci)]),
     "sfftb_get_filter": (_ci, [_PP, _ci, _vp, _vp]),
     "sfftb_set_filter": (_ci, [_PP, _ci, _vp, _vp]),

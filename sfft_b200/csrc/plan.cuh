@@ -65,6 +65,7 @@ struct PlanV12 {
   int *h_stage[kStageSlots] = {nullptr};
   cudaEvent_t stage_ev[kStageSlots] = {nullptr};
   int stage_next = 0;
+  int cur_nsig = 0;
   long long *h_counts = nullptr;   // pinned
 };
 
@@ -91,6 +92,9 @@ int v12_ensure_capacity(PlanImpl *p, int nsig);
 void v12_free(PlanImpl *p);
 int v12_draw(const PlanImpl *p, sfftb_draw *d);
 int v12_exec(PlanImpl *p, const cplx *d_in, long long stride, int nsig, const sfftb_draw *draws);
+void v12_shard_loops(const PlanImpl *p, int rank, int world, int *begin, int *end);
+int v12_shard_bucketize(PlanImpl *p, const cplx *d_in, const sfftb_draw *draw, int rank, int world);
+int v12_shard_finish(PlanImpl *p, int rank, int world);
 
 // timing helpers
 void timer_begin(PlanImpl *p);

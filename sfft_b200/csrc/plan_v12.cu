@@ -282,16 +282,13 @@ int v12_draw(const PlanImpl *p, sfftb_draw *d)
   return 0;
 }
 
-int v12_exec(PlanImpl *p, const cplx *d_in, long long stride, int nsig, const sfftb_draw *draws)
+// ---- transform stages (shared by the single-GPU driver and the sharded one) ----
+
+static int v12_stage_draws(PlanImpl *p, int nsig, const sfftb_draw *draws)
 {
   PlanV12 &v = p->v12;
   cudaStream_t st = p->stream;
-  const LoopGeom &g = v.geom;
-  const int loops = g.loops, num = v.B_thresh;
-  if (v12_ensure_capacity(p, nsig)) return -1;
-  timer_begin(p);
-
-  // ---- stage the draws ----
+  const int loops = v.geom.loops;
   const int slot = v.stage_next;
   v.stage_next = (v.stage_next + 1) % kStageSlots;
   SFFTB_CUDA(cudaEventSynchronize(v.stage_ev[slot]));
@@ -307,53 +304,80 @@ int v12_exec(PlanImpl *p, const cplx *d_in, long long stride, int nsig, const sf
   SFFTB_CUDA(cudaMemcpyAsync(v.d_stage, hs, sizeof(int) * (long long)nsig * v.ints_per_sig,
                              cudaMemcpyHostToDevice, st));
   SFFTB_CUDA(cudaEventRecord(v.stage_ev[slot], st));
-  const int *d_perm = v.d_stage;
-  const int *d_coff = v.d_stage + (long long)nsig * 2 * loops;
   SFFTB_CUDA(cudaMemsetAsync(v.d_voted_count, 0, sizeof(int) * nsig, st));
+  v.cur_nsig = nsig;
   timer_mark(p, "stage_draws");
+  return 0;
+}
 
-  // ---- Comb pre-filter (v2)  cf12.cc:483-512 ----
-  if (v.with_comb) {
-    const int W = v.W_Comb, logW = ilog2((unsigned)W), words = W >= 32 ? W / 32 : 1;
-    if (launch_comb_sample(d_in, stride, d_coff, v.Comb_loops, logW, p->logn, v.d_comb_xs,
-                           (long long)v.Comb_loops * W, nsig, st)) return -1;
-    if (fft_dit_inplace(v.d_comb_xs, logW, v.Comb_loops, W, nsig, (long long)v.Comb_loops * W,
-                        v.d_tw, v.log_twN, -1, st)) return -1;
-    SelectArgs sa;
-    sa.xs = v.d_comb_xs; sa.xs_stride = (long long)v.Comb_loops * W; sa.row_stride = W;
-    sa.logB = logW; sa.num = num;
-    sa.J = v.d_comb_J; sa.J_sig_stride = (long long)v.Comb_loops * num;
-    sa.bitmap = v.d_comb_bm; sa.bm_sig_stride = (long long)v.Comb_loops * words;
-    sa.gkeys = W > 16384 ? v.d_gkeys : nullptr; sa.gk_sig_stride = v.gkeys_per_sig;
-    sa.row_begin = 0; sa.row_step = 1;
-    if (launch_select(sa, v.Comb_loops, nsig, st)) return -1;
-    if (launch_comb_merge(v.d_comb_bm, v.Comb_loops, W, p->n / W, v.d_appr_bm, v.d_approved,
-                          v.d_num_comb, v.d_count, nsig, st)) return -1;
-    timer_mark(p, "comb");
-  }
+// Comb pre-filter (v2)  cf12.cc:483-512
+static int v12_stage_comb(PlanImpl *p, const cplx *d_in, long long stride, int nsig)
+{
+  PlanV12 &v = p->v12;
+  cudaStream_t st = p->stream;
+  if (!v.with_comb) return 0;
+  const int num = v.B_thresh, loops = v.geom.loops;
+  const int *d_coff = v.d_stage + (long long)nsig * 2 * loops;
+  const int W = v.W_Comb, logW = ilog2((unsigned)W), words = W >= 32 ? W / 32 : 1;
+  if (launch_comb_sample(d_in, stride, d_coff, v.Comb_loops, logW, p->logn, v.d_comb_xs,
+                         (long long)v.Comb_loops * W, nsig, st)) return -1;
+  if (fft_dit_inplace(v.d_comb_xs, logW, v.Comb_loops, W, nsig, (long long)v.Comb_loops * W,
+                      v.d_tw, v.log_twN, -1, st)) return -1;
+  SelectArgs sa;
+  sa.xs = v.d_comb_xs; sa.xs_stride = (long long)v.Comb_loops * W; sa.row_stride = W;
+  sa.logB = logW; sa.num = num;
+  sa.J = v.d_comb_J; sa.J_sig_stride = (long long)v.Comb_loops * num;
+  sa.bitmap = v.d_comb_bm; sa.bm_sig_stride = (long long)v.Comb_loops * words;
+  sa.gkeys = W > 16384 ? v.d_gkeys : nullptr; sa.gk_sig_stride = v.gkeys_per_sig;
+  sa.row_begin = 0; sa.row_step = 1;
+  if (launch_select(sa, v.Comb_loops, nsig, st)) return -1;
+  if (launch_comb_merge(v.d_comb_bm, v.Comb_loops, W, p->n / W, v.d_appr_bm, v.d_approved,
+                        v.d_num_comb, v.d_count, nsig, st)) return -1;
+  timer_mark(p, "comb");
+  return 0;
+}
 
-  // ---- permuted windowed gather  cf12.cc:222-261 ----
+// permuted windowed gather (cf12.cc:222-261) + bucket FFTs (cf12.cc:270-275) of loops [lb, le)
+static int v12_stage_bucketize(PlanImpl *p, const cplx *d_in, long long stride, int nsig, int lb, int le)
+{
+  PlanV12 &v = p->v12;
+  cudaStream_t st = p->stream;
+  const LoopGeom &g = v.geom;
+  if (le <= lb) return 0;
   GatherArgs ga;
   ga.x = d_in; ga.x_stride = stride;
   ga.taps[0] = v.filt[0].time; ga.taps[1] = v.filt[1].time;
-  ga.perm = d_perm; ga.xs = v.d_xs;
-  ga.loop_begin = 0; ga.loop_step = 1;
-  if (launch_gather(g, ga, loops, nsig, st)) return -1;
+  ga.perm = v.d_stage; ga.xs = v.d_xs;
+  ga.loop_begin = lb; ga.loop_step = 1;
+  if (launch_gather(g, ga, le - lb, nsig, st)) return -1;
   timer_mark(p, "gather");
 
-  // ---- bucket FFTs  cf12.cc:270-275 ----
+  const int loc_b = lb < v.loops_loc ? lb : v.loops_loc, loc_e = le < v.loops_loc ? le : v.loops_loc;
+  const int est_b = (lb > v.loops_loc ? lb : v.loops_loc) - v.loops_loc;
+  const int est_e = (le > v.loops_loc ? le : v.loops_loc) - v.loops_loc;
   if (v.B_loc == v.B_est) {
-    if (fft_dit_inplace(v.d_xs, g.logB[0], loops, v.B_loc, nsig, v.x_samp_size, v.d_tw, v.log_twN,
-                        -1, st)) return -1;
+    if (fft_dit_inplace(v.d_xs + (long long)lb * v.B_loc, g.logB[0], le - lb, v.B_loc, nsig,
+                        v.x_samp_size, v.d_tw, v.log_twN, -1, st)) return -1;
   } else {
-    if (fft_dit_inplace(v.d_xs, g.logB[0], v.loops_loc, v.B_loc, nsig, v.x_samp_size, v.d_tw,
-                        v.log_twN, -1, st)) return -1;
-    if (fft_dit_inplace(v.d_xs + (long long)v.loops_loc * v.B_loc, g.logB[1], v.loops_est, v.B_est,
-                        nsig, v.x_samp_size, v.d_tw, v.log_twN, -1, st)) return -1;
+    if (loc_e > loc_b &&
+        fft_dit_inplace(v.d_xs + (long long)loc_b * v.B_loc, g.logB[0], loc_e - loc_b, v.B_loc, nsig,
+                        v.x_samp_size, v.d_tw, v.log_twN, -1, st)) return -1;
+    if (est_e > est_b &&
+        fft_dit_inplace(v.d_xs + (long long)v.loops_loc * v.B_loc + (long long)est_b * v.B_est, g.logB[1],
+                        est_e - est_b, v.B_est, nsig, v.x_samp_size, v.d_tw, v.log_twN, -1, st)) return -1;
   }
   timer_mark(p, "bucket_fft");
+  return 0;
+}
 
-  // ---- |.|^2 + top-2k per location loop  cf12.cc:278-302 ----
+// |.|^2 + top-2k per location loop (cf12.cc:278-302), voting (:304-323), estimation (:341-419)
+static int v12_stage_finish(PlanImpl *p, int nsig, int slice_rank, int slice_world)
+{
+  PlanV12 &v = p->v12;
+  cudaStream_t st = p->stream;
+  const LoopGeom &g = v.geom;
+  const int num = v.B_thresh;
+  const int *d_perm = v.d_stage;
   const int words_loc = v.B_loc >= 32 ? v.B_loc / 32 : 1;
   SelectArgs sa;
   sa.xs = v.d_xs; sa.xs_stride = v.x_samp_size; sa.row_stride = v.B_loc;
@@ -365,7 +389,6 @@ int v12_exec(PlanImpl *p, const cplx *d_in, long long stride, int nsig, const sf
   if (launch_select(sa, v.loops_loc, nsig, st)) return -1;
   timer_mark(p, "select");
 
-  // ---- reverse-hash voting  cf12.cc:304-323 ----
   VoteArgs va;
   va.perm = d_perm;
   va.J = v.d_J; va.J_sig_stride = sa.J_sig_stride;
@@ -378,7 +401,6 @@ int v12_exec(PlanImpl *p, const cplx *d_in, long long stride, int nsig, const sf
   if (launch_vote(g, va, nsig, st)) return -1;
   timer_mark(p, "vote");
 
-  // ---- estimation  cf12.cc:341-419 ----
   EstimateArgs ea;
   ea.perm = d_perm;
   ea.xs = v.d_xs; ea.xs_stride = v.x_samp_size;
@@ -392,10 +414,52 @@ int v12_exec(PlanImpl *p, const cplx *d_in, long long stride, int nsig, const sf
   ea.num_comb = v.d_num_comb;
   ea.W = v.W_Comb; ea.n_over_W = v.with_comb ? p->n / v.W_Comb : 0;
   ea.out_loc = v.d_hit_loc; ea.out_val = v.d_hit_val; ea.out_cap = v.max_hits;
+  // only the v2 pre-filled list is worth slicing across GPUs; v1's hit order is not
+  // identical across ranks (atomic append), so v1 estimates every hit on every rank
+  const bool slice = slice_world > 1 && v.with_comb;
+  ea.slice_rank = slice ? slice_rank : 0;
+  ea.slice_world = slice ? slice_world : 1;
+  ea.slice_count = slice ? v.d_count : nullptr;
   if (launch_estimate(g, ea, nsig, v.max_hits, st)) return -1;
   timer_mark(p, "estimate");
   p->last_nsig = nsig;
   return 0;
 }
+
+int v12_exec(PlanImpl *p, const cplx *d_in, long long stride, int nsig, const sfftb_draw *draws)
+{
+  PlanV12 &v = p->v12;
+  if (v12_ensure_capacity(p, nsig)) return -1;
+  timer_begin(p);
+  if (v12_stage_draws(p, nsig, draws)) return -1;
+  if (v12_stage_comb(p, d_in, stride, nsig)) return -1;
+  if (v12_stage_bucketize(p, d_in, stride, nsig, 0, v.geom.loops)) return -1;
+  return v12_stage_finish(p, nsig, 0, 1);
+}
+
+// ---- multi-GPU sharding of one transform (include/sfft.h) ----
+
+void v12_shard_loops(const PlanImpl *p, int rank, int world, int *begin, int *end)
+{
+  const int loops = p->v12.geom.loops;
+  *begin = (int)((long long)loops * rank / world);
+  *end = (int)((long long)loops * (rank + 1) / world);
+}
+
+int v12_shard_bucketize(PlanImpl *p, const cplx *d_in, const sfftb_draw *draw, int rank, int world)
+{
+  PlanV12 &v = p->v12;
+  if (v12_ensure_capacity(p, 1)) return -1;
+  timer_begin(p);
+  if (v12_stage_draws(p, 1, draw)) return -1;
+  if (v12_stage_comb(p, d_in, p->n, 1)) return -1;       // tiny; replicated on every rank
+  // rows this rank does not own must be exactly zero for the sum over ranks
+  SFFTB_CUDA(cudaMemsetAsync(v.d_xs, 0, sizeof(cplx) * v.x_samp_size, p->stream));
+  int lb, le;
+  v12_shard_loops(p, rank, world, &lb, &le);
+  return v12_stage_bucketize(p, d_in, p->n, 1, lb, le);
+}
+
+int v12_shard_finish(PlanImpl *p, int rank, int world) { return v12_stage_finish(p, 1, rank, world); }
 
 }  // namespace sfftb

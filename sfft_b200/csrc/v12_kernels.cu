@@ -485,6 +485,13 @@ estimate_pair_kernel(LoopGeom g, EstimateArgs a, long long max_per_sig)
     total = a.count[s];
   }
   if (total > max_per_sig) total = max_per_sig;
+  // multi-GPU slice of the list: [lo, lo + total)
+  long long lo = 0;
+  if (a.slice_world > 1) {
+    lo = total * a.slice_rank / a.slice_world;
+    total = total * (a.slice_rank + 1) / a.slice_world - lo;
+  }
+  if (a.slice_count && blockIdx.x == 0 && threadIdx.x == 0) a.slice_count[s] = (int)total;
   const int *__restrict__ perm = a.perm + (long long)s * perm_stride(g.loops) + g.loops;   // ai[]
   const cplx *__restrict__ xs = a.xs + (long long)s * a.xs_stride;
   const bool imag = threadIdx.x & 1;
@@ -494,7 +501,7 @@ estimate_pair_kernel(LoopGeom g, EstimateArgs a, long long max_per_sig)
   for (long long base = (long long)blockIdx.x * 128; base < total; base += (long long)gridDim.x * 128) {
     const long long h = base + pair;
     const bool active = h < total;
-    const long long hc = active ? h : total - 1;
+    const long long hc = lo + (active ? h : total - 1);
     unsigned loc;
     if (a.approved) {
       const long long jj = hc / nc;
@@ -550,6 +557,12 @@ estimate_generic_kernel(LoopGeom g, EstimateArgs a, long long max_per_sig)
     total = a.count[s];
   }
   if (total > max_per_sig) total = max_per_sig;
+  long long lo = 0;
+  if (a.slice_world > 1) {
+    lo = total * a.slice_rank / a.slice_world;
+    total = total * (a.slice_rank + 1) / a.slice_world - lo;
+  }
+  if (a.slice_count && blockIdx.x == 0 && threadIdx.x == 0) a.slice_count[s] = (int)total;
   const int loops = g.loops;
   const int mid = (loops - 1) / 2;     // cf12.cc:406
   const int *__restrict__ perm = a.perm + (long long)s * perm_stride(g.loops) + g.loops;   // ai[]
@@ -557,12 +570,13 @@ estimate_generic_kernel(LoopGeom g, EstimateArgs a, long long max_per_sig)
   for (long long h = blockIdx.x * (long long)blockDim.x + threadIdx.x; h < total;
        h += (long long)gridDim.x * blockDim.x) {
     unsigned loc;
+    const long long hc = lo + h;
     if (a.approved) {
-      const long long jj = h / nc;
-      const int i = (int)(h - jj * nc);
+      const long long jj = hc / nc;
+      const int i = (int)(hc - jj * nc);
       loc = (unsigned)(jj * a.W + __ldg(&a.approved[(long long)s * a.approved_stride + i]));
     } else {
-      loc = (unsigned)a.hits[(long long)s * a.hits_cap + h];
+      loc = (unsigned)a.hits[(long long)s * a.hits_cap + hc];
     }
     double vr[kMaxLoops], vi[kMaxLoops];
     for (int j = 0; j < loops; j++)

@@ -64,6 +64,9 @@ struct EstimateArgs {
   const int *count;
   const int *approved;  long long approved_stride; const int *num_comb; int W, n_over_W;
   int *out_loc;         cplx *out_val;  long long out_cap;
+  // multi-GPU: this launch covers slice `slice_rank` of `slice_world` of the hit list and
+  // records the slice length in slice_count (null when the whole list is covered)
+  int slice_rank, slice_world; int *slice_count;
 };
 
 int launch_gather(const LoopGeom &g, const GatherArgs &a, int nloops, int nsig, cudaStream_t st);
