@@ -73,7 +73,25 @@ def build(force=False, verbose=False):
     link = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", HOST_CXX,
             "-o", OUT] + objs + ["-lm"]
     subprocess.check_call(link)
+    build_tools()
     return OUT
+
+
+def build_tools():
+    """The reference's three drivers over this library (tools/sfft_harness.cc) and the
+    HBM random-gather microbenchmarks."""
+    root = os.path.dirname(HERE)
+    tools = os.path.join(root, "tools")
+    src = os.path.join(tools, "sfft_harness.cc")
+    for mode, name in ((0, "sfft-timing"), (1, "sfft-verification"), (2, "sfft-timing_many")):
+        subprocess.check_call([HOST_CXX, "-O2", f"-DHARNESS_MODE={mode}", src, "-I", os.path.join(root, "include"),
+                               "-L", HERE, "-lsfft", f"-Wl,-rpath,{HERE}", "-Wl,-rpath,$ORIGIN/../sfft_b200",
+                               "-o", os.path.join(tools, name)])
+    for mb in ("random_gather", "ld_variants"):
+        cu = os.path.join(tools, "microbench", mb + ".cu")
+        if os.path.exists(cu):
+            subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",
+                                   "-ccbin", HOST_CXX, "-o", os.path.join(tools, "microbench", mb), cu])
 
 
 if __name__ == "__main__":
