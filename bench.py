@@ -37,8 +37,11 @@ WORKLOADS = {
     "C2": (2, 1 << 24, 1000, None, "sFFT v2 (Comb) exact k-sparse n=2^24 k=1000"),
     "C3": (3, 1 << 26, 2000, None, "sFFT v3 exact-sparse n=2^26 k=2000"),
     "C4": (1, 1 << 27, 500, 20.0, "sFFT v1 noisy 20 dB n=2^27 k=500"),
-    "C5": (1, 1 << 20, 100, None, "sFFT v1 n=2^20 k=100 batch"),
+    "C5": (1, 1 << 20, 100, None, "sFFT v1 n=2^20 k=100, sfft_exec_many batch of 256 signals per step"),
 }
+# signals transformed per step and per GPU (sfft_exec_many); BASELINE config 5 is a batch of
+# 4096 = 64 GiB of input, benchmarked here 256 signals (4 GiB) at a time
+BATCH = {"C5": 256}
 
 
 def env_int(name, default):
@@ -178,7 +181,7 @@ def run_reference_arm(args):
     rank = env_int("RANK", 0)
     if rank != 0:
         return
-    r = cpu_reference_run(args.workload, args.gpus, args.steps, args.warmup)
+    r = cpu_reference_run(args.workload, args.gpus * min(BATCH.get(args.workload, 1), 8), args.steps, args.warmup)
     version, n, k, snr_db, desc = WORKLOADS[args.workload]
     if "unavailable" in r:
         print(json.dumps({"impl": "reference", "unavailable": r["unavailable"]}))
@@ -268,10 +271,15 @@ def run_ours(args):
 
     # rotate over several distinct signals; each is >= L2-sized at the default workload,
     # smaller workloads additionally get an explicit L2 flush between steps
+    batch = BATCH.get(args.workload, 1)
     nsig_rot = max(2, min(4, (1 << 28) // n)) if n <= (1 << 26) else 1
-    signals = synth_signals(torch, n, k, nsig_rot, 1234 + rank, snr_db, dev)
+    if batch > 1:
+        nsig_rot = 1
+        signals = [torch.stack(synth_signals(torch, n, k, batch, 1234 + rank, snr_db, dev))]
+    else:
+        signals = synth_signals(torch, n, k, nsig_rot, 1234 + rank, snr_db, dev)
     flush = None
-    if n * 16 < 256 * 1024 * 1024:
+    if batch * n * 16 < 256 * 1024 * 1024:
         flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
 
     libc = C.CDLL(None)
@@ -279,7 +287,10 @@ def run_ours(args):
     libc.srand48(12345 + rank)
 
     def step(i):
-        plan.execute_device(signals[i % nsig_rot], None, sync=False)
+        if batch > 1:
+            plan.execute_many_device(signals[0], None, sync=False)
+        else:
+            plan.execute_device(signals[i % nsig_rot], None, sync=False)
 
     def barrier():
         if world > 1:
@@ -312,13 +323,16 @@ def run_ours(args):
     ms_steps = [a.elapsed_time(b) for a, b in ev]
     total_ms = sum(ms_steps)
     clocks = sampler.stop() if rank == 0 else None
-    count = plan.execute_device(signals[0], None, sync=True)
+    if batch > 1:
+        count = int(sum(plan.execute_many_device(signals[0], None, sync=True)) / batch)
+    else:
+        count = plan.execute_device(signals[0], None, sync=True)
 
     t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     total_ms_max = float(t.item())
-    value = world * args.steps * n / (total_ms_max * 1e-3) / 1e9
+    value = world * args.steps * batch * n / (total_ms_max * 1e-3) / 1e9
 
     # ---- per-stage device times (separate pass, events between stages) ----
     plan.stage_timing(True)
@@ -334,25 +348,37 @@ def run_ours(args):
     stages = {nm: sum(v) / len(v) for nm, v in acc.items()}
 
     # ---- e2e through the legacy host API (rank-local, all ranks concurrently) ----
-    h_in = L.sfft_malloc(16 * n)
-    h_out = L.sfft_malloc(16 * n)
+    e2e_batch = min(batch, 64)
+    h_in = [L.sfft_malloc(16 * n) for _ in range(e2e_batch)]
+    h_out = [L.sfft_malloc(16 * n) for _ in range(e2e_batch)]
     e2e_steps = max(1, min(args.steps, 10))
-    host_sig = signals[0].cpu().numpy()
-    C.memmove(h_in, host_sig.ctypes.data, 16 * n)
+    for i in range(e2e_batch):
+        src = signals[0][i] if batch > 1 else signals[0]
+        host_sig = src.cpu().numpy()
+        C.memmove(h_in[i], host_sig.ctypes.data, 16 * n)
+    in_arr = (C.c_void_p * e2e_batch)(*h_in)
+    out_arr = (C.c_void_p * e2e_batch)(*h_out)
+
+    def e2e_call():
+        if e2e_batch > 1:
+            L.sfft_exec_many(plan.sfft_plan, e2e_batch, in_arr, out_arr)
+        else:
+            L.sfft_exec(plan.sfft_plan, h_in[0], h_out[0])
+
     for _ in range(min(2, args.warmup)):
-        L.sfft_exec(plan.sfft_plan, h_in, h_out)
+        e2e_call()
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        L.sfft_exec(plan.sfft_plan, h_in, h_out)
+        e2e_call()
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
     te = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_value = world * e2e_steps * n / float(te.item()) / 1e9
-    L.sfft_free(h_in)
-    L.sfft_free(h_out)
+    e2e_value = world * e2e_steps * e2e_batch * n / float(te.item()) / 1e9
+    for ptr in h_in + h_out:
+        L.sfft_free(ptr)
 
     # ---- N > 1: ONE signal sharded over all ranks (loops split, one all-reduce) ----
     sharded = None
@@ -386,15 +412,22 @@ def run_ours(args):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s"
 
+        traffic = {}
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(args.workload, {})
+        except Exception:
+            pass
+
         def roof(stage):
             ms = stages.get(stage)
             if not ms:
                 return None
-            b = stage_bytes(info, stage, count)
+            b = batch * stage_bytes(info, stage, count)
             ach = b / (ms * 1e-3) / 1e9
             return {"kernel": stage, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": ach / hbm_peak, "traffic": None, "ms": ms, "algorithmic_bytes": b,
-                    "peak_source": peak_src}
+                    "frac": ach / hbm_peak, "traffic": traffic.get(stage), "ms": ms, "algorithmic_bytes": b,
+                    "peak_source": peak_src,
+                    "traffic_source": "ncu dram bytes per launch, profiles/r01_traffic.json" if stage in traffic else None}
 
         dominant = max(stages, key=stages.get) if stages else None
         line = {
@@ -403,15 +436,16 @@ def run_ours(args):
             "ms_per_step": total_ms_max / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {"workload": f"{args.workload}: {desc}", "n": n, "k": k, "version": version,
-                       "signals_per_gpu_per_step": 1,
-                       "cache": ("input %d MiB > L2, %d signals rotated" % (16 * n >> 20, nsig_rot))
+                       "signals_per_gpu_per_step": batch,
+                       "cache": ("input %d MiB > L2, %d signals rotated" % (16 * n * batch >> 20, nsig_rot))
                        + ("" if flush is None else ", 256 MiB L2 flush between steps"),
                        "recovered_coefficients": int(count),
                        "plan": {kk: info[kk] for kk in ("B_loc", "B_est", "loops_loc", "loops_est", "w_loc",
                                                        "w_est", "W_Comb", "Comb_loops", "x_samp_size")}},
-            "e2e": {"value": e2e_value, "unit": "Gsamples/s", "h2d_bytes_per_step": 16 * n,
-                    "d2h_bytes_per_step": 16 * n, "steps": e2e_steps,
-                    "api": "sfft_exec(plan, host_in, host_out), pinned buffers from sfft_malloc"},
+            "e2e": {"value": e2e_value, "unit": "Gsamples/s", "h2d_bytes_per_step": 16 * n * e2e_batch,
+                    "d2h_bytes_per_step": 16 * n * e2e_batch, "steps": e2e_steps,
+                    "api": ("sfft_exec_many(plan, %d, host_in[], host_out[])" % e2e_batch if e2e_batch > 1
+                            else "sfft_exec(plan, host_in, host_out)") + ", pinned buffers from sfft_malloc"},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": roof(dominant) if dominant else None,
@@ -424,7 +458,7 @@ def run_ours(args):
             line["loop_sharded_single_signal"] = sharded
         if world == 1 and not args.no_cpu_baseline:
             try:
-                line["cpu_baseline"] = cpu_reference_run(args.workload, 1, 1, 0, budget_s=90.0)
+                line["cpu_baseline"] = cpu_reference_run(args.workload, min(batch, 8), 1, 0, budget_s=90.0)
             except Exception as e:     # the baseline leg must not sink the bench line
                 line["cpu_baseline"] = {"unavailable": repr(e)}
         print(json.dumps(line))

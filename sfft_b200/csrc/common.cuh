@@ -72,6 +72,18 @@ __device__ __forceinline__ cplx ldg_stream(const cplx *p)
   return r;
 }
 
+// same, asking L2 to fill only 64 bytes around the sample instead of the whole 128-byte
+// line: halves DRAM traffic when neighbouring samples will not be wanted soon
+// (tools/microbench/ld_variants: 128 B -> 64 B of DRAM per random 16-byte read)
+__device__ __forceinline__ cplx ldg_stream64(const cplx *p)
+{
+  cplx r;
+  asm volatile("ld.global.nc.L1::no_allocate.L2::64B.v2.f64 {%0, %1}, [%2];"
+               : "=d"(r.x), "=d"(r.y)
+               : "l"(p));
+  return r;
+}
+
 __host__ __device__ __forceinline__ int ilog2(unsigned long long v)
 {
   int l = 0;

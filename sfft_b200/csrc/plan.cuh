@@ -59,6 +59,8 @@ struct PlanV12 {
   unsigned *d_appr_bm = nullptr;   // [cap][W/32]
   int *d_approved = nullptr;       // [cap][W]
   int *d_num_comb = nullptr;       // [cap]
+  cplx *d_V = nullptr;             // v2 structured estimation: [loops][max_comb][n/W] (single signal)
+  int max_comb = 0;
   // per-transform draws: a[loops], ai[loops] per signal, then comb offsets
   int *d_stage = nullptr;          // [cap * ints_per_sig]
   int ints_per_sig = 0;
@@ -66,6 +68,16 @@ struct PlanV12 {
   cudaEvent_t stage_ev[kStageSlots] = {nullptr};
   int stage_next = 0;
   int cur_nsig = 0;
+  // CUDA-graph replay of the single-signal transform: the kernel sequence is captured once;
+  // per call only the staged draw and the signal pointer (read indirectly) change
+  cudaGraphExec_t graph_exec = nullptr;
+  cudaGraph_t graph = nullptr;
+  int *h_gstage = nullptr;                 // pinned: draws
+  unsigned long long *h_gx = nullptr;      // pinned: signal pointer
+  unsigned long long *d_gx = nullptr;
+  cudaEvent_t g_ev = nullptr;              // staging buffers consumed
+  int plain_execs = 0;
+  int graph_kernels = 0;                   // kernels in one transform (for the launch counter)
   long long *h_counts = nullptr;   // pinned
 };
 

@@ -5,6 +5,7 @@
 // the kernels of v12_kernels.cu / fft.cu.
 #include <math.h>
 #include <stdlib.h>
+#include <stdint.h>
 #include <string.h>
 
 #include "fft.cuh"
@@ -191,10 +192,15 @@ int v12_build(PlanImpl *p)
 
 static void v12_free_scratch(PlanV12 &v)
 {
+  if (v.graph_exec) cudaGraphExecDestroy(v.graph_exec);
+  if (v.graph) cudaGraphDestroy(v.graph);
+  v.graph_exec = nullptr; v.graph = nullptr;
+
   cudaFree(v.d_xs); cudaFree(v.d_J); cudaFree(v.d_bitmap); cudaFree(v.d_gkeys);
   cudaFree(v.d_voted); cudaFree(v.d_voted_count); cudaFree(v.d_hit_loc); cudaFree(v.d_hit_val);
   cudaFree(v.d_count); cudaFree(v.d_comb_xs); cudaFree(v.d_comb_J); cudaFree(v.d_comb_bm);
   cudaFree(v.d_appr_bm); cudaFree(v.d_approved); cudaFree(v.d_num_comb); cudaFree(v.d_stage);
+  cudaFree(v.d_V); v.d_V = nullptr;
   for (int i = 0; i < kStageSlots; i++) {
     if (v.h_stage[i]) cudaFreeHost(v.h_stage[i]);
     v.h_stage[i] = nullptr;
@@ -237,6 +243,14 @@ int v12_ensure_capacity(PlanImpl *p, int nsig)
     SFFTB_CUDA(cudaMalloc(&v.d_approved, sizeof(int) * S * W));
     SFFTB_CUDA(cudaMalloc(&v.d_num_comb, sizeof(int) * S));
     if (W > 16384 && (long long)v.Comb_loops * W > gk) gk = (long long)v.Comb_loops * W;
+    v.max_comb = (int)((long long)v.Comb_loops * num < W ? (long long)v.Comb_loops * num : W);
+    if (nsig == 1 && v2_struct_supported(v.geom, ilog2((unsigned)W)) && !getenv("SFFTB_NO_V2_STRUCT")) {
+      // a failed allocation just leaves the generic estimator in charge
+      if (cudaMalloc(&v.d_V, sizeof(cplx) * (long long)v.geom.loops * v.max_comb * (p->n / W)) != cudaSuccess) {
+        cudaGetLastError();
+        v.d_V = nullptr;
+      }
+    }
   }
   v.gkeys_per_sig = gk;
   if (gk) SFFTB_CUDA(cudaMalloc(&v.d_gkeys, sizeof(unsigned long long) * S * gk));
@@ -255,6 +269,11 @@ void v12_free(PlanImpl *p)
   free_filter(&v.filt[1]);
   cudaFree(v.d_tw);
   v.d_tw = nullptr;
+  if (v.h_gstage) cudaFreeHost(v.h_gstage);
+  if (v.h_gx) cudaFreeHost(v.h_gx);
+  cudaFree(v.d_gx);
+  if (v.g_ev) cudaEventDestroy(v.g_ev);
+  v.h_gstage = nullptr; v.h_gx = nullptr; v.d_gx = nullptr; v.g_ev = nullptr;
   for (int i = 0; i < kStageSlots; i++) {
     if (v.stage_ev[i]) cudaEventDestroy(v.stage_ev[i]);
     v.stage_ev[i] = nullptr;
@@ -311,7 +330,7 @@ static int v12_stage_draws(PlanImpl *p, int nsig, const sfftb_draw *draws)
 }
 
 // Comb pre-filter (v2)  cf12.cc:483-512
-static int v12_stage_comb(PlanImpl *p, const cplx *d_in, long long stride, int nsig)
+static int v12_stage_comb(PlanImpl *p, const cplx *d_in, const unsigned long long *x_ind, long long stride, int nsig)
 {
   PlanV12 &v = p->v12;
   cudaStream_t st = p->stream;
@@ -319,7 +338,7 @@ static int v12_stage_comb(PlanImpl *p, const cplx *d_in, long long stride, int n
   const int num = v.B_thresh, loops = v.geom.loops;
   const int *d_coff = v.d_stage + (long long)nsig * 2 * loops;
   const int W = v.W_Comb, logW = ilog2((unsigned)W), words = W >= 32 ? W / 32 : 1;
-  if (launch_comb_sample(d_in, stride, d_coff, v.Comb_loops, logW, p->logn, v.d_comb_xs,
+  if (launch_comb_sample(d_in, x_ind, stride, d_coff, v.Comb_loops, logW, p->logn, v.d_comb_xs,
                          (long long)v.Comb_loops * W, nsig, st)) return -1;
   if (fft_dit_inplace(v.d_comb_xs, logW, v.Comb_loops, W, nsig, (long long)v.Comb_loops * W,
                       v.d_tw, v.log_twN, -1, st)) return -1;
@@ -338,14 +357,15 @@ static int v12_stage_comb(PlanImpl *p, const cplx *d_in, long long stride, int n
 }
 
 // permuted windowed gather (cf12.cc:222-261) + bucket FFTs (cf12.cc:270-275) of loops [lb, le)
-static int v12_stage_bucketize(PlanImpl *p, const cplx *d_in, long long stride, int nsig, int lb, int le)
+static int v12_stage_bucketize(PlanImpl *p, const cplx *d_in, const unsigned long long *x_ind, long long stride,
+                               int nsig, int lb, int le)
 {
   PlanV12 &v = p->v12;
   cudaStream_t st = p->stream;
   const LoopGeom &g = v.geom;
   if (le <= lb) return 0;
   GatherArgs ga;
-  ga.x = d_in; ga.x_stride = stride;
+  ga.x = d_in; ga.x_indirect = x_ind; ga.x_stride = stride;
   ga.taps[0] = v.filt[0].time; ga.taps[1] = v.filt[1].time;
   ga.perm = v.d_stage; ga.xs = v.d_xs;
   ga.loop_begin = lb; ga.loop_step = 1;
@@ -420,21 +440,107 @@ static int v12_stage_finish(PlanImpl *p, int nsig, int slice_rank, int slice_wor
   ea.slice_rank = slice ? slice_rank : 0;
   ea.slice_world = slice ? slice_world : 1;
   ea.slice_count = slice ? v.d_count : nullptr;
-  if (launch_estimate(g, ea, nsig, v.max_hits, st)) return -1;
+  if (v.with_comb && nsig == 1 && v.d_V) {
+    V2StructArgs sa2;
+    sa2.perm = d_perm; sa2.xs = v.d_xs;
+    sa2.fwin[0] = ea.fwin[0]; sa2.fwin[1] = ea.fwin[1];
+    sa2.fw_half[0] = ea.fw_half[0]; sa2.fw_half[1] = ea.fw_half[1];
+    sa2.fdr[0] = ea.fdr[0]; sa2.fdr[1] = ea.fdr[1];
+    sa2.approved = v.d_approved; sa2.num_comb = v.d_num_comb;
+    sa2.logW = ilog2((unsigned)v.W_Comb);
+    sa2.V = v.d_V;
+    sa2.out_loc = v.d_hit_loc; sa2.out_val = v.d_hit_val; sa2.out_cap = v.max_hits;
+    sa2.slice_rank = ea.slice_rank; sa2.slice_world = ea.slice_world; sa2.slice_count = ea.slice_count;
+    if (launch_v2_struct(g, sa2, v.max_comb, st)) return -1;
+  } else {
+    if (launch_estimate(g, ea, nsig, v.max_hits, st)) return -1;
+  }
   timer_mark(p, "estimate");
   p->last_nsig = nsig;
   return 0;
+}
+
+static void fill_stage(const PlanV12 &v, int *hs, int nsig, const sfftb_draw *draws)
+{
+  const int loops = v.geom.loops;
+  int *h_coff = hs + (long long)nsig * 2 * loops;
+  for (int s = 0; s < nsig; s++) {
+    const sfftb_draw &d = draws[s];
+    memcpy(hs + (long long)s * 2 * loops, d.a, sizeof(int) * loops);
+    memcpy(hs + (long long)s * 2 * loops + loops, d.ai, sizeof(int) * loops);
+    for (int c = 0; c < v.Comb_loops; c++) h_coff[(long long)s * v.Comb_loops + c] = d.comb_offset[c];
+  }
+}
+
+// Single-signal transform replayed from a CUDA graph: ~10 kernels + 2 small copies become
+// one launch, which is what a 2-60 us transform needs (SURVEY 7 "Latency").
+static int v12_exec_graph(PlanImpl *p, const cplx *d_in, const sfftb_draw *draw)
+{
+  PlanV12 &v = p->v12;
+  cudaStream_t st = p->stream;
+  if (!v.graph_exec) {
+    if (!v.h_gstage) {
+      SFFTB_CUDA(cudaHostAlloc(&v.h_gstage, sizeof(int) * v.ints_per_sig, cudaHostAllocDefault));
+      SFFTB_CUDA(cudaHostAlloc(&v.h_gx, sizeof(unsigned long long), cudaHostAllocDefault));
+      SFFTB_CUDA(cudaMalloc(&v.d_gx, sizeof(unsigned long long)));
+      SFFTB_CUDA(cudaEventCreateWithFlags(&v.g_ev, cudaEventDisableTiming));
+    }
+    SFFTB_CUDA(cudaStreamSynchronize(st));
+    SFFTB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = 0;
+    if (cudaMemcpyAsync(v.d_stage, v.h_gstage, sizeof(int) * v.ints_per_sig, cudaMemcpyHostToDevice, st) != cudaSuccess) rc = -1;
+    if (cudaMemcpyAsync(v.d_gx, v.h_gx, sizeof(unsigned long long), cudaMemcpyHostToDevice, st) != cudaSuccess) rc = -1;
+    if (cudaEventRecordWithFlags(v.g_ev, st, cudaEventRecordExternal) != cudaSuccess) rc = -1;
+    if (cudaMemsetAsync(v.d_voted_count, 0, sizeof(int), st) != cudaSuccess) rc = -1;
+    if (!rc) rc = v12_stage_comb(p, nullptr, v.d_gx, p->n, 1);
+    if (!rc) rc = v12_stage_bucketize(p, nullptr, v.d_gx, p->n, 1, 0, v.geom.loops);
+    if (!rc) rc = v12_stage_finish(p, 1, 0, 1);
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(st, &g);
+    if (rc || e != cudaSuccess || !g) {
+      if (g) cudaGraphDestroy(g);
+      cudaGetLastError();
+      set_error("CUDA graph capture of the transform failed");
+      return -1;
+    }
+    v.graph = g;
+    SFFTB_CUDA(cudaGraphInstantiate(&v.graph_exec, v.graph, 0));
+  }
+  SFFTB_CUDA(cudaEventSynchronize(v.g_ev));      // previous replay has consumed the staging buffers
+  fill_stage(v, v.h_gstage, 1, draw);
+  *v.h_gx = (unsigned long long)(uintptr_t)d_in;
+  SFFTB_CUDA(cudaGraphLaunch(v.graph_exec, st));
+  g_launches += v.graph_kernels;
+  p->last_nsig = 1;
+  return 0;
+}
+
+static bool graphs_enabled()
+{
+  static int on = -1;
+  if (on < 0) on = getenv("SFFTB_NO_GRAPH") ? 0 : 1;
+  return on == 1;
 }
 
 int v12_exec(PlanImpl *p, const cplx *d_in, long long stride, int nsig, const sfftb_draw *draws)
 {
   PlanV12 &v = p->v12;
   if (v12_ensure_capacity(p, nsig)) return -1;
+  // the first transforms run launch by launch (lazy one-time kernel attributes are set there),
+  // then single-signal transforms are replayed from a captured graph
+  if (nsig == 1 && !p->timer.enabled && graphs_enabled() && v.plain_execs >= 1) {
+    if (v12_exec_graph(p, d_in, draws) == 0) return 0;
+    v.plain_execs = -1000000;      // capture failed once: stay on the plain path
+  }
+  v.plain_execs++;
   timer_begin(p);
+  const long long launches0 = g_launches;
   if (v12_stage_draws(p, nsig, draws)) return -1;
-  if (v12_stage_comb(p, d_in, stride, nsig)) return -1;
-  if (v12_stage_bucketize(p, d_in, stride, nsig, 0, v.geom.loops)) return -1;
-  return v12_stage_finish(p, nsig, 0, 1);
+  if (v12_stage_comb(p, d_in, nullptr, stride, nsig)) return -1;
+  if (v12_stage_bucketize(p, d_in, nullptr, stride, nsig, 0, v.geom.loops)) return -1;
+  if (v12_stage_finish(p, nsig, 0, 1)) return -1;
+  v.graph_kernels = (int)(g_launches - launches0);
+  return 0;
 }
 
 // ---- multi-GPU sharding of one transform (include/sfft.h) ----
@@ -452,12 +558,12 @@ int v12_shard_bucketize(PlanImpl *p, const cplx *d_in, const sfftb_draw *draw, i
   if (v12_ensure_capacity(p, 1)) return -1;
   timer_begin(p);
   if (v12_stage_draws(p, 1, draw)) return -1;
-  if (v12_stage_comb(p, d_in, p->n, 1)) return -1;       // tiny; replicated on every rank
+  if (v12_stage_comb(p, d_in, nullptr, p->n, 1)) return -1;       // tiny; replicated on every rank
   // rows this rank does not own must be exactly zero for the sum over ranks
   SFFTB_CUDA(cudaMemsetAsync(v.d_xs, 0, sizeof(cplx) * v.x_samp_size, p->stream));
   int lb, le;
   v12_shard_loops(p, rank, world, &lb, &le);
-  return v12_stage_bucketize(p, d_in, p->n, 1, lb, le);
+  return v12_stage_bucketize(p, d_in, nullptr, p->n, 1, lb, le);
 }
 
 int v12_shard_finish(PlanImpl *p, int rank, int world) { return v12_stage_finish(p, 1, rank, world); }

@@ -25,6 +25,9 @@ __device__ __forceinline__ long long loop_offset(const LoopGeom &g, int j)
 constexpr int kGatherThreads = 256;
 constexpr int kGatherUnroll = 8;
 
+// SPARSE: the loops together touch only a small fraction of the signal, so a 128-byte
+// line fill mostly fetches samples nobody will read: ask for 64-byte fills.
+template <bool SPARSE>
 __global__ void __launch_bounds__(kGatherThreads)
 gather_kernel(LoopGeom g, GatherArgs a)
 {
@@ -38,7 +41,8 @@ gather_kernel(LoopGeom g, GatherArgs a)
 
   const int w = est ? g.w[1] : g.w[0];
   const cplx *__restrict__ taps = est ? a.taps[1] : a.taps[0];
-  const cplx *__restrict__ x = a.x + (long long)s * a.x_stride;
+  const cplx *__restrict__ x =
+      (a.x_indirect ? reinterpret_cast<const cplx *>(*a.x_indirect) : a.x) + (long long)s * a.x_stride;
   const unsigned ai = (unsigned)a.perm[(long long)s * perm_stride(g.loops) + g.loops + j];
   const unsigned mask = (unsigned)g.n_mask;
 
@@ -52,7 +56,7 @@ gather_kernel(LoopGeom g, GatherArgs a)
 #pragma unroll
     for (int u = 0; u < kGatherUnroll; u++) {
       const unsigned ii = i + u * B;
-      xv[u] = ldg_stream(x + id);
+      xv[u] = SPARSE ? ldg_stream64(x + id) : ldg_stream(x + id);
       tv[u] = __ldg(taps + (ii < (unsigned)w ? ii : 0u));
       id = (id + stepB) & mask;
     }
@@ -76,7 +80,10 @@ int launch_gather(const LoopGeom &g, const GatherArgs &a, int nloops, int nsig, 
   if (nloops <= 0) return 0;
   const int maxlog = g.logB[0] > g.logB[1] ? g.logB[0] : g.logB[1];
   dim3 grid((unsigned)ceil_div(1ll << maxlog, kGatherThreads), (unsigned)nloops, (unsigned)nsig);
-  gather_kernel<<<grid, kGatherThreads, 0, st>>>(g, a);
+  // fraction of the signal's samples the gathers of one transform read
+  const double cover = ((double)g.loops_loc * g.w[0] + (double)(g.loops - g.loops_loc) * g.w[1]) / ((double)g.n_mask + 1.0);
+  if (cover < 0.25) gather_kernel<true><<<grid, kGatherThreads, 0, st>>>(g, a);
+  else gather_kernel<false><<<grid, kGatherThreads, 0, st>>>(g, a);
   SFFTB_LAUNCH_CHECK();
   return 0;
 }
@@ -139,7 +146,9 @@ select_kernel(SelectArgs a)
     int run_d = -1;
     unsigned run_c = 0;
     for (int e = 0; e < mine; e++) {
-      const unsigned long long key = keys[key_slot(lo + e, in_smem)];
+      // the histogram does not care which keys a thread counts: shared-memory keys are
+      // read chunk-wise (padded, conflict-free), global ones strided so warps coalesce
+      const unsigned long long key = in_smem ? keys[key_slot(lo + e, true)] : keys[e * kSelectThreads + tid];
       const bool match = pass == 0 ? true : ((key >> (shift + 8)) == prefix);
       if (match) {
         const int d = (int)((key >> shift) & 255ull);
@@ -614,12 +623,159 @@ int launch_estimate(const LoopGeom &g, const EstimateArgs &a, int nsig, long lon
 }
 
 // ---------------------------------------------------------------------------
+// v2 structured estimation (see v12_kernels.cuh)
+// ---------------------------------------------------------------------------
+constexpr int kV2Threads = 1024;
+constexpr int kV2Chunks = 8;          // residue chunks per (loop, class)
+
+__device__ __forceinline__ void v2_slice(const V2StructArgs &a, long long total, long long &lo, long long &hi)
+{
+  lo = 0; hi = total;
+  if (a.slice_world > 1) {
+    lo = total * a.slice_rank / a.slice_world;
+    hi = total * (a.slice_rank + 1) / a.slice_world;
+  }
+}
+
+__global__ void __launch_bounds__(kV2Threads)
+v2_values_kernel(LoopGeom g, V2StructArgs a)
+{
+  extern __shared__ cplx subrow[];
+  const int j = blockIdx.z, cls = blockIdx.y, chunk = blockIdx.x;
+  const bool est = j >= g.loops_loc;
+  const int logB = est ? g.logB[1] : g.logB[0];
+  const int logseg = g.logn - logB;
+  const int logq = a.logW - logseg;            // q = W / seg buckets per W positions
+  if (cls >= (1 << logq)) return;
+  const int logNW = g.logn - a.logW;           // n/W = buckets per class
+  const int NW = 1 << logNW;
+  const int nc = a.num_comb[0];
+  long long lo, hi;
+  v2_slice(a, (long long)nc * NW, lo, hi);
+  if (hi <= lo) return;
+  const int i_first = (int)(lo >> logNW), i_last = (int)((hi - 1) >> logNW);   // residues this launch needs
+  const int span = i_last - i_first + 1;
+  const int i0 = i_first + (int)((long long)span * chunk / kV2Chunks);
+  const int i1 = i_first + (int)((long long)span * (chunk + 1) / kV2Chunks);
+  if (i1 <= i0) return;
+
+  const cplx *__restrict__ row = a.xs + loop_offset(g, j);
+  for (int t = threadIdx.x; t < NW; t += kV2Threads) subrow[t] = row[cls + (t << logq)];
+  __syncthreads();
+
+  const unsigned mask = (unsigned)g.n_mask;
+  const unsigned ai = (unsigned)a.perm[g.loops + j];
+  const unsigned m = ai & (unsigned)(NW - 1);                // ai*W mod n = W * (ai mod n/W)
+  const int seg = 1 << logseg;
+  const cplx *__restrict__ fw = est ? a.fwin[1] : a.fwin[0];
+  const double2 *__restrict__ fdr = est ? a.fdr[1] : a.fdr[0];
+  const int half = est ? a.fw_half[1] : a.fw_half[0];
+  for (int i = i0; i < i1; i++) {
+    const unsigned r = (unsigned)__ldg(&a.approved[i]);
+    const unsigned pos = (unsigned)(((unsigned long long)ai * r) & mask);          // jj = 0
+    unsigned bucket = pos >> logseg;
+    int dist = (int)(pos & (unsigned)(seg - 1));
+    if (dist > seg / 2) {                                                           // cf12.cc:373-377
+      bucket = (bucket + 1) & ((1u << logB) - 1u);
+      dist -= seg;
+    }
+    if ((int)(bucket & ((1u << logq) - 1u)) != cls) continue;                       // other class's CTA
+    const unsigned t0 = bucket >> logq;
+    const cplx f = __ldg(&fw[half - dist]);
+    const double2 dr = __ldg(&fdr[half - dist]);
+    cplx *__restrict__ dst = a.V + (((long long)j * nc + i) << logNW);
+    for (int jj = threadIdx.x; jj < NW; jj += kV2Threads) {
+      const cplx sv = subrow[(t0 + m * (unsigned)jj) & (unsigned)(NW - 1)];
+      const double ac = __dmul_rn(sv.x, f.x), bd = __dmul_rn(sv.y, f.y);
+      const double ad = __dmul_rn(sv.x, f.y), bc = __dmul_rn(sv.y, f.x);
+      dst[jj] = make_double2(div_by_rcp_rn(__dadd_rn(ac, bd), dr.x, dr.y),
+                             div_by_rcp_rn(__dsub_rn(ad, bc), dr.x, dr.y));       // :388-398
+    }
+  }
+}
+
+template <int L>
+__global__ void __launch_bounds__(256, 2)
+v2_median_kernel(LoopGeom g, V2StructArgs a)
+{
+  const int logNW = g.logn - a.logW;
+  const int nc = a.num_comb[0];
+  long long lo, hi;
+  v2_slice(a, (long long)nc << logNW, lo, hi);
+  if (a.slice_count && blockIdx.x == 0 && threadIdx.x == 0) a.slice_count[0] = (int)(hi - lo);
+  for (long long idx = lo + blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < hi;
+       idx += (long long)gridDim.x * blockDim.x) {
+    const int i = (int)(idx >> logNW);
+    const unsigned jj = (unsigned)(idx & ((1ll << logNW) - 1));
+    double vr[L], vi[L];
+#pragma unroll
+    for (int j = 0; j < L; j++) {
+      const cplx v = a.V[(((long long)j * nc + i) << logNW) + jj];
+      vr[j] = v.x;
+      vi[j] = v.y;
+    }
+    const double re = MedianNet<L>::run(vr);
+    const double im = MedianNet<L>::run(vi);
+    const long long o = idx - lo;
+    a.out_loc[o] = (int)((jj << a.logW) + (unsigned)__ldg(&a.approved[i]));      // cf12.cc:508-511
+    a.out_val[o] = make_double2(re, im);
+  }
+}
+
+bool v2_struct_supported(const LoopGeom &g, int logW)
+{
+  for (int grp = 0; grp < 2; grp++) {
+    const int logseg = g.logn - g.logB[grp];
+    if (logW < logseg) return false;                 // W must be a multiple of the bucket width
+  }
+  const int logNW = g.logn - logW;
+  return logNW >= 5 && logNW <= 13 && g.loops >= 2 && g.loops <= 32;   // sub-row <= 128 KB
+}
+
+int launch_v2_struct(const LoopGeom &g, const V2StructArgs &a, int max_comb, cudaStream_t st)
+{
+  const int logNW = g.logn - a.logW;
+  int logq_max = 0;
+  for (int grp = 0; grp < 2; grp++) {
+    const int lq = a.logW - (g.logn - g.logB[grp]);
+    if (lq > logq_max) logq_max = lq;
+  }
+  const size_t smem = sizeof(cplx) << logNW;
+  static bool attr_set = false;
+  if (!attr_set) {
+    SFFTB_CUDA(cudaFuncSetAttribute(v2_values_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    (int)(sizeof(cplx) << 13)));
+    attr_set = true;
+  }
+  dim3 grid(kV2Chunks, 1u << logq_max, (unsigned)g.loops);
+  v2_values_kernel<<<grid, kV2Threads, smem, st>>>(g, a);
+  SFFTB_LAUNCH_CHECK();
+  long long blocks = (((long long)max_comb << logNW) + 255) / 256;
+  if (blocks > 148ll * 16) blocks = 148ll * 16;
+  switch (g.loops) {
+#define SFFTB_V2M_CASE(N) case N: v2_median_kernel<N><<<(unsigned)blocks, 256, 0, st>>>(g, a); break;
+    SFFTB_V2M_CASE(2) SFFTB_V2M_CASE(3) SFFTB_V2M_CASE(4) SFFTB_V2M_CASE(5) SFFTB_V2M_CASE(6)
+    SFFTB_V2M_CASE(7) SFFTB_V2M_CASE(8) SFFTB_V2M_CASE(9) SFFTB_V2M_CASE(10) SFFTB_V2M_CASE(11)
+    SFFTB_V2M_CASE(12) SFFTB_V2M_CASE(13) SFFTB_V2M_CASE(14) SFFTB_V2M_CASE(15) SFFTB_V2M_CASE(16)
+    SFFTB_V2M_CASE(17) SFFTB_V2M_CASE(18) SFFTB_V2M_CASE(19) SFFTB_V2M_CASE(20) SFFTB_V2M_CASE(21)
+    SFFTB_V2M_CASE(22) SFFTB_V2M_CASE(23) SFFTB_V2M_CASE(24) SFFTB_V2M_CASE(25) SFFTB_V2M_CASE(26)
+    SFFTB_V2M_CASE(27) SFFTB_V2M_CASE(28) SFFTB_V2M_CASE(29) SFFTB_V2M_CASE(30) SFFTB_V2M_CASE(31)
+    SFFTB_V2M_CASE(32)
+#undef SFFTB_V2M_CASE
+    default: set_error("launch_v2_struct: unsupported loop count"); return -1;
+  }
+  SFFTB_LAUNCH_CHECK();
+  return 0;
+}
+
+// ---------------------------------------------------------------------------
 // K6  Comb pre-filter (v2)   (cf12.cc:49-82, :483-512)
 // ---------------------------------------------------------------------------
-__global__ void comb_sample_kernel(const cplx *__restrict__ x, long long x_stride,
-                                   const int *__restrict__ comb_off, int comb_loops, int logW,
-                                   int logn, cplx *cxs, long long cxs_stride)
+__global__ void comb_sample_kernel(const cplx *__restrict__ x_direct, const unsigned long long *x_indirect,
+                                   long long x_stride, const int *__restrict__ comb_off, int comb_loops,
+                                   int logW, int logn, cplx *cxs, long long cxs_stride)
 {
+  const cplx *__restrict__ x = x_indirect ? reinterpret_cast<const cplx *>(*x_indirect) : x_direct;
   const int c = blockIdx.y, s = blockIdx.z;
   const unsigned i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (1u << logW)) return;
@@ -629,12 +785,12 @@ __global__ void comb_sample_kernel(const cplx *__restrict__ x, long long x_strid
   cxs[(long long)s * cxs_stride + ((long long)c << logW) + bitrev(i, logW)] = v;
 }
 
-int launch_comb_sample(const cplx *x, long long x_stride, const int *comb_off, int comb_loops,
-                       int logW, int logn, cplx *cxs, long long cxs_stride, int nsig,
-                       cudaStream_t st)
+int launch_comb_sample(const cplx *x, const unsigned long long *x_indirect, long long x_stride,
+                       const int *comb_off, int comb_loops, int logW, int logn, cplx *cxs,
+                       long long cxs_stride, int nsig, cudaStream_t st)
 {
   dim3 grid((unsigned)ceil_div(1ll << logW, 256), (unsigned)comb_loops, (unsigned)nsig);
-  comb_sample_kernel<<<grid, 256, 0, st>>>(x, x_stride, comb_off, comb_loops, logW, logn, cxs,
+  comb_sample_kernel<<<grid, 256, 0, st>>>(x, x_indirect, x_stride, comb_off, comb_loops, logW, logn, cxs,
                                            cxs_stride);
   SFFTB_LAUNCH_CHECK();
   return 0;

@@ -27,6 +27,7 @@ __host__ __device__ __forceinline__ long long perm_stride(int loops) { return 2l
 
 struct GatherArgs {
   const cplx *x;            // signals
+  const unsigned long long *x_indirect;   // if set: device slot holding the signal pointer (CUDA-graph replay)
   long long x_stride;       // elements between signals
   const cplx *taps[2];
   const int *perm;
@@ -74,13 +75,34 @@ int launch_select(const SelectArgs &a, int nrows, int nsig, cudaStream_t st);
 int launch_vote(const LoopGeom &g, const VoteArgs &a, int nsig, cudaStream_t st);
 int launch_estimate(const LoopGeom &g, const EstimateArgs &a, int nsig, long long max_per_sig,
                     cudaStream_t st);
+// ---- v2 structured estimation ---------------------------------------------------
+// v2's result list is {jj*W + r : r approved, jj < n/W} (cf12.cc:505-512).  For a fixed
+// loop j and residue r, ai_j*(jj*W + r) walks the buckets of ONE residue class modulo
+// q = W/(n/B) with a constant offset inside the bucket, visiting each of the n/W buckets
+// of that class exactly once.  So instead of 16.4 M x 20 random 16-byte L2 reads
+// (request-rate bound), phase 1 stages one class sub-row (n/W buckets) in shared memory
+// and streams the quotients out coalesced, V[j][i][jj]; phase 2 reads them back
+// coalesced and takes the medians.  Same arithmetic, same results.
+struct V2StructArgs {
+  const int *perm;                 // a[loops], ai[loops]
+  const cplx *xs;                  // bucket spectra of this signal
+  const cplx *fwin[2]; int fw_half[2]; const double2 *fdr[2];
+  const int *approved; const int *num_comb;
+  int logW;                        // W_Comb = 2^logW
+  cplx *V;                         // [loops][num_comb][n/W]
+  int *out_loc; cplx *out_val; long long out_cap;
+  int slice_rank, slice_world; int *slice_count;
+};
+bool v2_struct_supported(const LoopGeom &g, int logW);
+int launch_v2_struct(const LoopGeom &g, const V2StructArgs &a, int max_comb, cudaStream_t st);
+
 int launch_filter_den(const cplx *fwin, int len, double2 *fdr, cudaStream_t st);
 long long run_div_check(unsigned long long seed, long long count);
 
 // v2: xs[c][bitrev(i)] = x[offset_c + i*sigma]   (cf12.cc:61-67)
-int launch_comb_sample(const cplx *x, long long x_stride, const int *comb_off, int comb_loops,
-                       int logW, int logn, cplx *cxs, long long cxs_stride, int nsig,
-                       cudaStream_t st);
+int launch_comb_sample(const cplx *x, const unsigned long long *x_indirect, long long x_stride,
+                       const int *comb_off, int comb_loops, int logW, int logn, cplx *cxs,
+                       long long cxs_stride, int nsig, cudaStream_t st);
 // v2: union of the per-loop selections -> sorted residue list, its size, and the
 // size of the pre-filled hit list (cf12.cc:492-512)
 int launch_comb_merge(const unsigned *loop_bitmaps, int comb_loops, int W, int n_over_W,
