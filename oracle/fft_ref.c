@@ -39,8 +39,28 @@ ocplx *orc_twiddle_table(long n)
 {
   long h = n / 2 > 0 ? n / 2 : 1;
   ocplx *t = (ocplx *)malloc((size_t)h * sizeof(ocplx));
-  for (long k = 0; k < n / 2; k++)
-    orc_twiddle(k, n, &t[k].re, &t[k].im);
+  if (n <= ORC_TW_DIRECT_MAX) {
+    for (long k = 0; k < n / 2; k++)
+      orc_twiddle(k, n, &t[k].re, &t[k].im);
+  } else {
+    /* Large transforms (the plan builder's n-point and Bluestein FFTs): a twiddle is
+     * DEFINED as the rounded product of a coarse and a fine factor,
+     *     W_n^k = A[k >> 14] * F[k & 16383],  A[m] = W_n^(16384 m),  F[l] = W_n^l,
+     * each factor by the octant rule.  Two small tables instead of n/2 libm calls, and a
+     * definition the CUDA plan builder can evaluate bit-identically on the fly. */
+    const long lo = ORC_TW_FINE, nhi = (n / 2 + lo - 1) / lo;
+    ocplx *A = (ocplx *)malloc((size_t)nhi * sizeof(ocplx));
+    ocplx *F = (ocplx *)malloc((size_t)lo * sizeof(ocplx));
+    for (long m = 0; m < nhi; m++) orc_twiddle(m * lo, n, &A[m].re, &A[m].im);
+    for (long l = 0; l < lo; l++) orc_twiddle(l, n, &F[l].re, &F[l].im);
+    for (long k = 0; k < n / 2; k++) {
+      const ocplx a = A[k / lo], f = F[k % lo];
+      const double p0 = a.re * f.re, p1 = a.im * f.im, p2 = a.re * f.im, p3 = a.im * f.re;
+      t[k].re = p0 - p1;
+      t[k].im = p2 + p3;
+    }
+    free(A); free(F);
+  }
   if (n < 2) { t[0].re = 1.0; t[0].im = -0.0; }
   return t;
 }

@@ -30,6 +30,11 @@ extern "C" {
 
 typedef struct { double re, im; } ocplx;
 
+/* transforms up to this size take every twiddle straight from the octant rule; larger
+ * ones use the two-factor definition in orc_twiddle_table() */
+#define ORC_TW_DIRECT_MAX (1L << 17)
+#define ORC_TW_FINE (1L << 14)
+
 /* e^{-2 pi i k / n} for n a power of two, 0 <= k < n/2, by octant reduction:
  * only angles in [0, pi/4] are handed to libm, so values at multiples of
  * pi/4 are exact and the table is symmetric. */

@@ -44,3 +44,21 @@ void sfftb_host_ramp_step(int w, int n, double *re, double *im)
   *re = creal(step);
   *im = cimag(step);
 }
+
+/* Bluestein chirp e^{sign*pi*i*j^2/n}, j < n, with the argument reduced exactly (j^2 mod 2n)
+ * before it reaches libm: the definition the oracle pins in fft_ref.c:bluestein. */
+void sfftb_host_chirp(int n, int sign, double *out_re_im)
+{
+  for (long j = 0; j < n; j++) {
+    long long q = ((long long)j * j) % (2 * (long long)n);
+    double ang = M_PI * (double)q / (double)n;
+    out_re_im[2 * j] = cos(ang);
+    out_re_im[2 * j + 1] = (sign < 0 ? -1.0 : 1.0) * sin(ang);
+  }
+}
+
+/* |re + i*im| as the reference takes it (cabs, src/filters.cc:128) */
+double sfftb_host_cabs(double re, double im)
+{
+  return cabs(CMPLX(re, im));
+}

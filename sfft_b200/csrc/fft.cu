@@ -3,6 +3,8 @@
 
 #include <math.h>
 
+#include <vector>
+
 namespace sfftb {
 
 // ---------------------------------------------------------------------------
@@ -45,22 +47,38 @@ void host_twiddle_levels(long n, cplx *out)
     for (long k = 0; k < h; k++) host_twiddle(k * (n / (2 * h)), n, &out[h - 1 + k].x, &out[h - 1 + k].y);
 }
 
+void host_twiddle_factors(long n, std::vector<cplx> &coarse, std::vector<cplx> &fine)
+{
+  const long lo = 1L << 14, nhi = (n / 2 + lo - 1) / lo;
+  coarse.resize((size_t)nhi);
+  fine.resize((size_t)lo);
+  for (long m = 0; m < nhi; m++) host_twiddle(m * lo, n, &coarse[(size_t)m].x, &coarse[(size_t)m].y);
+  for (long l = 0; l < lo; l++) host_twiddle(l, n, &fine[(size_t)l].x, &fine[(size_t)l].y);
+}
+
 // ---------------------------------------------------------------------------
 // one pass = stages [s0, s0+ns) of the DIT graph on a tile of 2^ns rows (stride
 // 2^s0 elements) by 2^logT adjacent columns, staged in shared memory
 // ---------------------------------------------------------------------------
 constexpr int kFftThreads = 256;
+constexpr int kTwFineLog = 14;         // == log2(ORC_TW_FINE) of the oracle's definition
 constexpr int kMaxTileLog = 11;        // 2048 points = 32 KB of shared memory
 constexpr int kLaterPassStages = 8;    // keeps >= 8 adjacent columns (128 B) per row
 
 // TABLE: `tw` is the level-ordered twiddle table (host_twiddle_levels).  The first
 // pass (s0 == 0) copies levels [0, ns) next to the tile in shared memory; later
 // passes read their (column-contiguous) twiddles through L1/L2.
-template <bool TABLE>
+// MODE 0: sincospi on the fly (accuracy reference only)
+// MODE 1: level-ordered table `tw`
+// MODE 2: two-factor twiddles for large transforms, W_N^K = A[K >> 14] * F[K & 16383]
+//         (`tw` = A, `tw2` = F, N = 2^log_twN): the oracle's definition for N > 2^17
+template <int MODE>
 __global__ void __launch_bounds__(kFftThreads)
 fft_pass_kernel(cplx *base, int s0, int ns, int logT, long long fft_stride,
-                long long sig_stride, const cplx *__restrict__ tw, int log_twN, int sign)
+                long long sig_stride, const cplx *__restrict__ tw, const cplx *__restrict__ tw2,
+                int log_twN, int sign)
 {
+  constexpr bool TABLE = MODE == 1;
   extern __shared__ cplx tile[];
   cplx *stw = tile + (1 << (ns + logT));      // only used when TABLE && s0 == 0
   const int T = 1 << logT;
@@ -95,6 +113,9 @@ fft_pass_kernel(cplx *base, int s0, int ns, int logT, long long fft_stride,
       cplx w;
       if (TABLE) {
         w = s0 == 0 ? stw[(1 << s) - 1 + (int)k] : __ldg(&tw[(1ull << s) - 1ull + k]);
+      } else if (MODE == 2) {
+        const unsigned long long K = k << (log_twN - s - 1);
+        w = cmul_rn(__ldg(&tw[K >> kTwFineLog]), __ldg(&tw2[K & ((1ull << kTwFineLog) - 1ull)]));
       } else {
         double sn, cs;
         sincospi((double)k / (double)(1ull << s), &sn, &cs);
@@ -120,9 +141,20 @@ int fft_dit_inplace(cplx *base, int logN, int nfft, long long fft_stride, int ns
                     long long sig_stride, const cplx *tw, int log_twN, int sign,
                     cudaStream_t st)
 {
+  return fft_dit_inplace_ex(base, logN, nfft, fft_stride, nsig, sig_stride, tw, nullptr, log_twN, sign, st);
+}
+
+int fft_dit_inplace_ex(cplx *base, int logN, int nfft, long long fft_stride, int nsig,
+                       long long sig_stride, const cplx *tw, const cplx *tw_fine, int log_twN, int sign,
+                       cudaStream_t st)
+{
   if (logN <= 0 || nfft <= 0 || nsig <= 0) return 0;
-  if (tw && log_twN < logN) {
+  if (tw && !tw_fine && log_twN < logN) {
     set_error("fft_dit_inplace: twiddle table smaller than the transform");
+    return -1;
+  }
+  if (tw_fine && log_twN != logN) {
+    set_error("fft_dit_inplace: two-factor twiddles are per transform size");
     return -1;
   }
   int s0 = 0;
@@ -140,19 +172,22 @@ int fft_dit_inplace(cplx *base, int logN, int nfft, long long fft_stride, int ns
     const long long tiles = 1ll << (logN - ns - logT);
     dim3 grid((unsigned)tiles, (unsigned)nfft, (unsigned)nsig);
     size_t smem = sizeof(cplx) << (ns + logT);
-    if (tw && s0 == 0) smem += sizeof(cplx) << ns;
+    if (tw && !tw_fine && s0 == 0) smem += sizeof(cplx) << ns;
     static bool attr_set = false;
     if (!attr_set) {
-      SFFTB_CUDA(cudaFuncSetAttribute(fft_pass_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+      SFFTB_CUDA(cudaFuncSetAttribute(fft_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                       (int)(2 * (sizeof(cplx) << kMaxTileLog))));
       attr_set = true;
     }
-    if (tw)
-      fft_pass_kernel<true><<<grid, kFftThreads, smem, st>>>(base, s0, ns, logT, fft_stride,
-                                                            sig_stride, tw, log_twN, sign);
+    if (tw && tw_fine)
+      fft_pass_kernel<2><<<grid, kFftThreads, smem, st>>>(base, s0, ns, logT, fft_stride, sig_stride, tw,
+                                                         tw_fine, log_twN, sign);
+    else if (tw)
+      fft_pass_kernel<1><<<grid, kFftThreads, smem, st>>>(base, s0, ns, logT, fft_stride, sig_stride, tw,
+                                                         nullptr, log_twN, sign);
     else
-      fft_pass_kernel<false><<<grid, kFftThreads, smem, st>>>(base, s0, ns, logT, fft_stride,
-                                                             sig_stride, tw, log_twN, sign);
+      fft_pass_kernel<0><<<grid, kFftThreads, smem, st>>>(base, s0, ns, logT, fft_stride, sig_stride, tw,
+                                                         nullptr, log_twN, sign);
     SFFTB_LAUNCH_CHECK();
     s0 += ns;
   }

@@ -13,6 +13,8 @@
 // the plan builder's n-point transforms use sincospi() on the fly instead.
 #pragma once
 
+#include <vector>
+
 #include "common.cuh"
 
 namespace sfftb {
@@ -32,6 +34,15 @@ void host_twiddle_levels(long n, cplx *out /* max(n-1, 1) entries */);
 int fft_dit_inplace(cplx *base, int logN, int nfft, long long fft_stride, int nsig,
                     long long sig_stride, const cplx *tw, int log_twN, int sign,
                     cudaStream_t st);
+
+// Transforms larger than 2^17 points (the plan builder's) take their twiddles from the
+// oracle's two-factor definition W_N^K = coarse[K >> 14] * fine[K & 16383] (one rounded
+// complex product), both factors by the octant rule at size N = 2^logN.
+constexpr int kTwDirectMaxLog = 17;
+void host_twiddle_factors(long n, std::vector<cplx> &coarse, std::vector<cplx> &fine);
+int fft_dit_inplace_ex(cplx *base, int logN, int nfft, long long fft_stride, int nsig,
+                       long long sig_stride, const cplx *tw, const cplx *tw_fine, int log_twN, int sign,
+                       cudaStream_t st);
 
 // out[bitrev(i)] = in[i] (out-of-place)
 int bitrev_permute(const cplx *in, cplx *out, int logN, cudaStream_t st);

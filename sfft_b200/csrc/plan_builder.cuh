@@ -17,6 +17,12 @@ struct DeviceFilter {
   double2 *fdr = nullptr; // [2*fw_half + 1]: (|f|^2, RN(1/|f|^2)), refreshed by filter_refresh()
 };
 
+struct FilterSpec {
+  double lobefrac, tolerance;
+  int b;         // boxcar width in frequency bins
+  int fw_half;   // half-width of the response window to keep
+};
+
 // w for (lobefrac, tolerance)   (src/filters.cc:72-74)
 int filter_width(double lobefrac, double tolerance);
 
@@ -24,6 +30,9 @@ int filter_width(double lobefrac, double tolerance);
 // frequency bins (src/filters.cc:70-86 then :109-160).
 int build_filter(int logn, double lobefrac, double tolerance, int b, int fw_half, DeviceFilter *out,
                  cudaStream_t st);
+// all (one or two) filters of a plan at once: shared windows are built once and the
+// sequential chains of every filter run concurrently
+int build_filters(int logn, int count, const FilterSpec *specs, DeviceFilter **outs, cudaStream_t st);
 void free_filter(DeviceFilter *f);
 // recompute the derived tables after fwin changed (plan build, sfftb_set_filter)
 int filter_refresh(DeviceFilter *f, cudaStream_t st);

@@ -156,8 +156,9 @@ int v12_build(PlanImpl *p)
   // filters (src/sfft.cc:355-364): only n/B+1 response entries are ever read
   // (cf12.cc:371-385), so keep the window [-n/2B, +n/2B]
   const int half_loc = (n / v.B_loc) / 2, half_est = (n / v.B_est) / 2;
-  if (build_filter(p->logn, v.lobe_loc, v.tol_loc, v.b_loc, half_loc, &v.filt[0], st)) return -1;
-  if (build_filter(p->logn, v.lobe_est, v.tol_est, v.b_est, half_est, &v.filt[1], st)) return -1;
+  FilterSpec specs[2] = {{v.lobe_loc, v.tol_loc, v.b_loc, half_loc}, {v.lobe_est, v.tol_est, v.b_est, half_est}};
+  DeviceFilter *outs[2] = {&v.filt[0], &v.filt[1]};
+  if (build_filters(p->logn, 2, specs, outs, st)) return -1;
   v.geom.w[0] = v.filt[0].w;
   v.geom.w[1] = v.filt[1].w;
 

@@ -599,8 +599,11 @@ estimate_generic_kernel(LoopGeom g, EstimateArgs a, long long max_per_sig)
 int launch_estimate(const LoopGeom &g, const EstimateArgs &a, int nsig, long long max_per_sig,
                     cudaStream_t st)
 {
+  // the hit count is only known on the device: size the grid for a full machine and let
+  // the kernel stride; in a batch every signal gets its share of that machine
   long long blocks = (max_per_sig + 127) / 128;
-  const long long cap = 148ll * 16;
+  long long cap = 148ll * 16 / nsig;
+  if (cap < 8) cap = 8;
   if (blocks > cap) blocks = cap;
   if (blocks < 1) blocks = 1;
   dim3 grid((unsigned)blocks, (unsigned)nsig);

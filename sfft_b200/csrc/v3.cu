@@ -730,8 +730,10 @@ int v3_build(PlanImpl *p, int n_req, int k)
   // response entries read: +-n/2B around 0 and the same one bucket up/down (:375-379, :612-616)
   const int half1 = 3 * (int)(n / v.B_g1) / 2 + 2, half2 = 3 * (int)(n / v.B_g2) / 2 + 2;
   const int cap1 = (int)n / 2 - 1;
-  if (build_filter(p->logn, 0.5 / BB, 1.e-8, b_g1, half1 < cap1 ? half1 : cap1, &v.filt[0], p->stream)) return -1;
-  if (build_filter(p->logn, 0.5 / BB2, 1.e-8, b_g2, half2 < cap1 ? half2 : cap1, &v.filt[1], p->stream)) return -1;
+  FilterSpec specs[2] = {{0.5 / BB, 1.e-8, b_g1, half1 < cap1 ? half1 : cap1},
+                         {0.5 / BB2, 1.e-8, b_g2, half2 < cap1 ? half2 : cap1}};
+  DeviceFilter *outs[2] = {&v.filt[0], &v.filt[1]};
+  if (build_filters(p->logn, 2, specs, outs, p->stream)) return -1;
   if (v.filt[0].w / v.B_g1 < 1 || v.filt[1].w / v.B_g2 < 1 || v.filt[1].w + 2 >= (int)n) {
     set_error("sfft_make_plan(v3): window shorter than one bucket sweep (reference asserts, cf3.cc:221)");
     return -1;

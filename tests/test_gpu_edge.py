@@ -1,0 +1,130 @@
+"""Edge cases of the transform path, GPU vs oracle through the C ABI: degenerate inputs
+(all zeros -> every magnitude ties at the cutoff; dense noise -> nothing is sparse),
+the smallest and some larger documented shapes, repeated transforms on one plan
+(reseeded and not), and plans of different versions living side by side (the
+reference's process-global mode flags, src/common.cc:22-23, forbid that)."""
+import numpy as np
+import pytest
+
+from util import bits_equal, rel_l2
+
+pytestmark = pytest.mark.gpu
+torch = pytest.importorskip("torch")
+
+
+def make_plan(n, k, version):
+    import sfft_b200.sfft as m
+    return m.sfft(n, k, version, strict_parameters=False)
+
+
+def fwin_from_full(freq, half):
+    n = freq.size
+    return np.ascontiguousarray(freq[(np.arange(-half, half + 1) + n) % n])
+
+
+def inject(plan, op):
+    for which, (t, f, B) in enumerate((("time_loc", "freq_loc", op.B_loc), ("time_est", "freq_est", op.B_est))):
+        plan.set_filter(which, op.arr(t), fwin_from_full(op.arr(f), (op.n // B) // 2))
+
+
+def gpu_vs_oracle(plan, op, oracle_mod, x, seed48):
+    oracle_mod.seed(17, seed48)
+    cnt = plan.execute_device(torch.from_numpy(np.ascontiguousarray(x)).cuda(), None)
+    loc, val = plan.result()
+    oracle_mod.seed(17, seed48)
+    out = op.exec(x)
+    o = np.argsort(loc, kind="stable")
+    return loc[o], val[o], out
+
+
+@pytest.mark.parametrize("version", [1, 2])
+def test_all_zero_signal_exercises_the_tie_rule(oracle_mod, version):
+    n, k = 16384, 50
+    p, op = make_plan(n, k, version), oracle_mod.Plan(n, k, version)
+    inject(p, op)
+    x = np.zeros(n, dtype=np.complex128)
+    loc, val, out = gpu_vs_oracle(p, op, oracle_mod, x, 1)
+    # every bucket magnitude is 0: the top-2k are the first 2k indices (src/utils.cc:145-155)
+    J = p.debug_fetch("J", np.int32, op.loops_loc * op.B_thresh).reshape(op.loops_loc, op.B_thresh)
+    assert np.array_equal(J[0], np.arange(op.B_thresh))
+    assert np.array_equal(J.ravel(), op.arr("J")[: J.size])
+    voted = np.sort(p.debug_fetch("voted", np.int32, n))
+    assert np.array_equal(voted, np.flatnonzero(op.arr("score") >= op.loops_thresh))
+    assert np.all(val == 0) and np.all(out == 0)
+    p.close(); op.free()
+
+
+def test_v3_all_zero_signal(oracle_mod):
+    n, k = 16384, 50
+    p, op = make_plan(n, k, 3), oracle_mod.Plan(n, k, 3)
+    x = np.zeros(n, dtype=np.complex128)
+    loc, val, out = gpu_vs_oracle(p, op, oracle_mod, x, 1)
+    assert loc.size == 0 and np.all(out == 0)
+    p.close(); op.free()
+
+
+@pytest.mark.parametrize("version", [1, 2])
+def test_dense_noise_input_still_matches(oracle_mod, version):
+    n, k = 32768, 50
+    rng = np.random.default_rng(5)
+    x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+    p, op = make_plan(n, k, version), oracle_mod.Plan(n, k, version)
+    inject(p, op)
+    loc, val, out = gpu_vs_oracle(p, op, oracle_mod, x, 2)
+    want = np.flatnonzero(out).astype(np.int32)
+    assert np.array_equal(loc, want)
+    assert bits_equal(val, out[want])
+    p.close(); op.free()
+
+
+@pytest.mark.parametrize("version,n,k", [(1, 8192, 50), (2, 8192, 50), (3, 8192, 50), (1, 1 << 22, 500),
+                                         (2, 1 << 19, 50), (1, 1 << 21, 2000), (3, 1 << 18, 16)])
+def test_more_shapes(oracle_mod, version, n, k):
+    x, xf = oracle_mod.generate_input(n, k, 404)
+    p, op = make_plan(n, k, version), oracle_mod.Plan(n, k, version)
+    loc, val, out = gpu_vs_oracle(p, op, oracle_mod, x, 6)
+    nz = val != 0
+    want = np.flatnonzero(out).astype(np.int32)
+    assert np.array_equal(loc[nz], want)
+    assert rel_l2(val[nz], out[want]) < 1e-9
+    p.close(); op.free()
+
+
+def test_repeated_transforms_and_coexisting_plans(oracle_mod):
+    n, k = 65536, 50
+    x, _ = oracle_mod.generate_input(n, k, 9)
+    plans = {v: make_plan(n, k, v) for v in (1, 2, 3)}       # all alive at once
+    oracles = {v: oracle_mod.Plan(n, k, v) for v in (1, 2, 3)}
+    for rep in range(3):                                      # graph replay kicks in from the 2nd call
+        for v in (2, 1, 3, 1, 2):
+            loc, val, out = gpu_vs_oracle(plans[v], oracles[v], oracle_mod, x, 100 + rep)
+            nz = val != 0
+            want = np.flatnonzero(out).astype(np.int32)
+            assert np.array_equal(loc[nz], want), (rep, v)
+            assert rel_l2(val[nz], out[want]) < 1e-9
+    # without reseeding the libc state advances exactly as the reference's would
+    oracle_mod.seed(17, 1)
+    a = [plans[1].execute_device(torch.from_numpy(x).cuda(), None) for _ in range(3)]
+    oracle_mod.seed(17, 1)
+    b = [int(np.count_nonzero(oracles[1].exec(x))) for _ in range(3)]
+    assert a == b
+    for v in (1, 2, 3):
+        plans[v].close(); oracles[v].free()
+
+
+def test_exec_many_device_batch_matches_single(oracle_mod):
+    n, k, num = 1 << 17, 50, 7
+    p, op = make_plan(n, k, 1), oracle_mod.Plan(n, k, 1)
+    inject(p, op)
+    xs = np.stack([oracle_mod.generate_input(n, k, 300 + i)[0] for i in range(num)])
+    oracle_mod.seed(17, 2)
+    counts = p.execute_many_device(torch.from_numpy(xs).cuda(), None)
+    oracle_mod.seed(17, 2)
+    for i in range(num):
+        out = op.exec(xs[i])
+        loc, val = p.result(i)
+        o = np.argsort(loc, kind="stable")
+        want = np.flatnonzero(out).astype(np.int32)
+        assert counts[i] == want.size and np.array_equal(loc[o], want)
+        assert bits_equal(val[o], out[want])
+    p.close(); op.free()

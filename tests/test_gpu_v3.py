@@ -48,8 +48,8 @@ def test_v3_plan_and_filters(oracle_mod, n, k):
         assert info[key] == getattr(op, key), key
     for which, (t, f) in enumerate((("filtert1", "filterf1"), ("filtert2", "filterf2"))):
         gt, gf = p.get_filter(which)
-        assert rel_l2(gt, op.arr(t)) < 1e-11
-        assert rel_l2(gf, fwin_from_full(op.arr(f), gf.size // 2)) < 1e-11
+        assert gt.tobytes() == op.arr(t).tobytes()
+        assert gf.tobytes() == fwin_from_full(op.arr(f), gf.size // 2).tobytes()
     p.close()
     op.free()
 
