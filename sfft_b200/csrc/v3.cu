@@ -56,6 +56,7 @@ struct PlanV3 {
   int *d_count = nullptr;          // [cap]
   int *d_rounds = nullptr;         // [cap]
   int *d_draw = nullptr;           // [cap][8]
+  long long *d_prof = nullptr;     // [cap][8] cycle counters of the peeling phases
   int *h_draw[kStageSlots] = {nullptr};
   cudaEvent_t ev[kStageSlots] = {nullptr};
   int next_slot = 0;
@@ -179,6 +180,7 @@ struct PeelArgs {
   int *ans_key; cplx *ans_val;
   int *count, *rounds;
   const cplx *fwin1, *fwin2;
+  long long *prof;      // per-signal cycle counters of the peeling phases (8 slots)
 };
 
 struct PeelCtx {
@@ -232,124 +234,176 @@ __device__ __forceinline__ cplx cdiv_smith(cplx x, cplx y)
   return make_double2(rx, ry);
 }
 
-// block-wide ordered append: every thread may contribute one (key, val); returns new total
-__device__ int ordered_append(bool have, int key, cplx val, int base, int *keys, cplx *vals, int cap,
-                              unsigned *warp_tot)
+// block-wide exclusive scan of one int per thread; `total` is the block sum
+__device__ int block_scan_excl(int v, int &total, unsigned *warp_tot)
 {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned bal = __ballot_sync(0xffffffffu, have);
-  if (lane == 0) warp_tot[warp] = __popc(bal);
-  __syncthreads();
-  unsigned off = 0, tot = 0;
-  for (int w = 0; w < kPeelThreads / 32; w++) {
-    const unsigned c = warp_tot[w];
-    if (w < warp) off += c;
-    tot += c;
+  int incl = v;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int u = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += u;
   }
-  if (have) {
-    const int pos = base + (int)off + __popc(bal & ((1u << lane) - 1u));
-    if (pos < cap) { keys[pos] = key; vals[pos] = val; }
+  if (lane == 31) warp_tot[warp] = (unsigned)incl;
+  __syncthreads();
+  if (warp == 0) {
+    const int t = (int)warp_tot[lane];
+    int sc = t;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const int u = __shfl_up_sync(0xffffffffu, sc, off);
+      if (lane >= off) sc += u;
+    }
+    warp_tot[lane] = (unsigned)(sc - t);
+    if (lane == 31) warp_tot[32] = (unsigned)sc;
   }
   __syncthreads();
-  return base + (int)tot;
+  const int excl = (int)warp_tot[warp] + incl - v;
+  total = (int)warp_tot[32];
+  __syncthreads();
+  return excl;
 }
 
-// computefourier-3.0.cc:642-776
-__device__ int decode_mansour(const PeelCtx &c, unsigned *warp_tot)
+__device__ int block_sum(int v, unsigned *warp_tot)
+{
+  int total;
+  block_scan_excl(v, total, warp_tot);
+  return total;
+}
+
+// computefourier-3.0.cc:642-776, one bucket
+__device__ __forceinline__ bool decode_one_mansour(const PeelCtx &c, int bk, cplx s0, cplx s1, int &key, cplx &val)
 {
   const V3Geom &g = c.g;
   const double PI2 = 2 * M_PI, N_OVER_PI2 = (double)g.n / PI2, PI2_OVER_N = PI2 / (double)g.n;
   const unsigned FREQ_MASK = ((unsigned)(g.n - 1)) & ~((unsigned)g.W - 1u);
   const double NORM = 1. / (double)g.W, NORM2 = NORM * NORM;
-  const cplx *p0 = c.samp + man_base(g), *p1 = p0 + g.W;
-  int found = 0;
-  for (int base = 0; base < g.W; base += kPeelThreads) {
-    const int bk = base + threadIdx.x;
-    bool have = false;
-    int key = 0;
-    cplx val = make_double2(0, 0);
-    if (bk < g.W) {
-      const cplx s0 = p0[bk], s1 = p1[bk];
-      const double e0 = __dadd_rn(__dmul_rn(s0.x, s0.x), __dmul_rn(s0.y, s0.y));
-      const double e1 = __dadd_rn(__dmul_rn(s1.x, s1.x), __dmul_rn(s1.y, s1.y));
-      const double zero_check = __dadd_rn(__dmul_rn(e0, NORM2), __dmul_rn(e1, NORM2));
-      if (zero_check > 1e-8) {
-        const double c0 = __dmul_rn(e0, NORM2), c1 = __dmul_rn(e1, NORM2);
-        const double d0 = atan2(s0.y * NORM, s0.x * NORM), d1 = atan2(s1.y * NORM, s1.x * NORM);
-        const double inv = 1. / c0;
-        const double bb = c1 * inv - 1;
-        const double error = bb * bb;
-        if (error < g.n * 1e-10 && c0 > 0.01) {
-          const double slope = d1 - d0;
-          const int freq1 = (int)llrint(slope * N_OVER_PI2);
-          const int freq3 = (int)(((unsigned)freq1 & FREQ_MASK) | (unsigned)bk);
-          const int freq_offset = (int)((unsigned)freq3 * (unsigned)c.off);     // 32-bit wrap, :743
-          const double phase = d0 - PI2_OVER_N * freq_offset;
-          const double mag = sqrt(c0);
-          double sn, cs;
-          sincos(phase, &sn, &cs);
-          have = true;
-          key = freq3;
-          val = make_double2(mag * cs, mag * sn);
-        }
-      }
-    }
-    found = ordered_append(have, key, val, found, c.est_key, c.est_val, g.est_cap, warp_tot);
-  }
-  return found < g.est_cap ? found : g.est_cap;
+  const double e0 = __dadd_rn(__dmul_rn(s0.x, s0.x), __dmul_rn(s0.y, s0.y));
+  const double e1 = __dadd_rn(__dmul_rn(s1.x, s1.x), __dmul_rn(s1.y, s1.y));
+  const double zero_check = __dadd_rn(__dmul_rn(e0, NORM2), __dmul_rn(e1, NORM2));
+  if (!(zero_check > 1e-8)) return false;
+  const double c0 = __dmul_rn(e0, NORM2), c1 = __dmul_rn(e1, NORM2);
+  const double d0 = atan2(s0.y * NORM, s0.x * NORM), d1 = atan2(s1.y * NORM, s1.x * NORM);
+  const double inv = 1. / c0;
+  const double bb = c1 * inv - 1;
+  const double error = bb * bb;
+  if (!(error < g.n * 1e-10 && c0 > 0.01)) return false;
+  const double slope = d1 - d0;
+  const int freq1 = (int)llrint(slope * N_OVER_PI2);
+  const int freq3 = (int)(((unsigned)freq1 & FREQ_MASK) | (unsigned)bk);
+  const int freq_offset = (int)((unsigned)freq3 * (unsigned)c.off);     // 32-bit wrap, :743
+  const double phase = d0 - PI2_OVER_N * freq_offset;
+  const double mag = sqrt(c0);
+  double sn, cs;
+  sincos(phase, &sn, &cs);
+  key = freq3;
+  val = make_double2(mag * cs, mag * sn);
+  return true;
 }
 
-// computefourier-3.0.cc:484-640
-__device__ int decode_gauss(const PeelCtx &c, int which /*1: first window, 2: permuted*/, unsigned *warp_tot)
+// computefourier-3.0.cc:484-640, one bucket
+__device__ __forceinline__ bool decode_one_gauss(const PeelCtx &c, int which, int bk, cplx s0, cplx s1, int &key,
+                                                 cplx &val)
 {
   const V3Geom &g = c.g;
   const int B = which == 1 ? g.B1 : g.B2;
   const int a = which == 1 ? 1 : c.a, b = which == 1 ? 0 : c.b;
   const cplx *fwin = which == 1 ? c.fwin1 : c.fwin2;
   const int half = which == 1 ? g.fw_half1 : g.fw_half2;
-  const cplx *p0 = c.samp + (which == 1 ? g1_base(g) : g2_base(g)), *p1 = p0 + B;
   const double PI2 = 2 * M_PI, N_OVER_PI2 = (double)g.n / PI2;
   const double PI2_A_OFFSET_OVER_N = PI2 * a * c.goff / (double)g.n;
   const double BUCKETS_OVER_N = (double)B / (double)g.n;
   const unsigned n1 = (unsigned)(g.n - 1), Bm = (unsigned)(B - 1);
   const unsigned N_OVER_BUCKETS = (unsigned)(g.n / B);
+  double c0 = __dadd_rn(__dmul_rn(s0.x, s0.x), __dmul_rn(s0.y, s0.y));
+  const double c1 = __dadd_rn(__dmul_rn(s1.x, s1.x), __dmul_rn(s1.y, s1.y));
+  if (!(__dadd_rn(c0, c1) > 1e-8)) return false;
+  const double d0 = atan2(s0.y, s0.x), d1 = atan2(s1.y, s1.x);
+  const double error_b = c1 / c0 - 1;
+  double error = error_b * error_b;
+  error /= (double)g.n;
+  if (!(error < 1e-12 && c0 > 0.01)) return false;
+  const double slope = d1 - d0;
+  int freq = (int)llrint(N_OVER_PI2 * slope) + g.n;
+  freq = (int)((unsigned)freq & n1);
+  const unsigned hashed_to = (unsigned)llrint(freq * BUCKETS_OVER_N) & Bm;
+  if (hashed_to != (unsigned)bk) return false;
+  const double phase = d0 - PI2_A_OFFSET_OVER_N * freq;
+  c0 = sqrt(c0);
+  double sn, cs;
+  sincos(phase, &sn, &cs);
+  cplx v = make_double2(c0 * cs, c0 * sn);
+  const int dist = (int)((hashed_to * N_OVER_BUCKETS - (unsigned)freq + (unsigned)g.n) & n1);
+  v = cdiv_smith(v, fwin_at(fwin, half, g.n, dist));
+  const unsigned pf = (unsigned)(((unsigned long long)(unsigned)freq * (unsigned)a) & n1);   // timesmod
+  key = (int)((pf - (unsigned)b + (unsigned)g.n) & n1);
+  val = v;
+  return true;
+}
+
+// Decode every bucket of one filter (which: 0 aliasing, 1 first window, 2 permuted window)
+// and list what was found in ascending bucket order, as the reference's loops do.
+// Phase 1: all buckets in parallel; a found (key, value) is parked at its bucket index and
+// flagged in a shared bit map.  Phase 2: one block scan over the flag words places the
+// entries.  Two barriers per 64 Ki buckets instead of two per 1024.
+constexpr int kFlagWords = 2048;
+__device__ int decode_filter(const PeelCtx &c, int which, unsigned *warp_tot, unsigned *sflags)
+{
+  const V3Geom &g = c.g;
+  const int nb = which == 0 ? g.W : (which == 1 ? g.B1 : g.B2);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  int *park_key = c.t_slot;          // free between peel steps
+  cplx *park_val = c.t_delta;
   int found = 0;
-  for (int base = 0; base < B; base += kPeelThreads) {
-    const int bk = base + threadIdx.x;
-    bool have = false;
-    int key = 0;
-    cplx val = make_double2(0, 0);
-    if (bk < B) {
-      const cplx s0 = p0[bk], s1 = p1[bk];
-      double c0 = __dadd_rn(__dmul_rn(s0.x, s0.x), __dmul_rn(s0.y, s0.y));
-      const double c1 = __dadd_rn(__dmul_rn(s1.x, s1.x), __dmul_rn(s1.y, s1.y));
-      if (__dadd_rn(c0, c1) > 1e-8) {
-        const double d0 = atan2(s0.y, s0.x), d1 = atan2(s1.y, s1.x);
-        const double error_b = c1 / c0 - 1;
-        double error = error_b * error_b;
-        error /= (double)g.n;
-        if (error < 1e-12 && c0 > 0.01) {
-          const double slope = d1 - d0;
-          int freq = (int)llrint(N_OVER_PI2 * slope) + g.n;
-          freq = (int)((unsigned)freq & n1);
-          const unsigned hashed_to = (unsigned)llrint(freq * BUCKETS_OVER_N) & Bm;
-          if (hashed_to == (unsigned)bk) {
-            const double phase = d0 - PI2_A_OFFSET_OVER_N * freq;
-            c0 = sqrt(c0);
-            double sn, cs;
-            sincos(phase, &sn, &cs);
-            cplx v = make_double2(c0 * cs, c0 * sn);
-            const int dist = (int)((hashed_to * N_OVER_BUCKETS - (unsigned)freq + (unsigned)g.n) & n1);
-            v = cdiv_smith(v, fwin_at(fwin, half, g.n, dist));
-            const unsigned pf = (unsigned)(((unsigned long long)(unsigned)freq * (unsigned)a) & n1);   // timesmod
-            have = true;
-            key = (int)((pf - (unsigned)b + (unsigned)g.n) & n1);
-            val = v;
-          }
-        }
+  for (int sbase = 0; sbase < nb; sbase += kFlagWords * 32) {
+    const int span = nb - sbase < kFlagWords * 32 ? nb - sbase : kFlagWords * 32;
+    const cplx *p0 = c.samp + (which == 0 ? man_base(g) : (which == 1 ? g1_base(g) : g2_base(g)));
+    const cplx *p1 = p0 + nb;
+    constexpr int kAhead = 4;          // loads of several chunks in flight: one CTA has little else to hide latency
+    for (int cb0 = 0; cb0 < span; cb0 += kAhead * kPeelThreads) {
+      cplx s0[kAhead], s1[kAhead];
+#pragma unroll
+      for (int u = 0; u < kAhead; u++) {
+        const int rel = cb0 + u * kPeelThreads + tid;
+        if (rel < span) { s0[u] = p0[sbase + rel]; s1[u] = p1[sbase + rel]; }
+      }
+#pragma unroll
+      for (int u = 0; u < kAhead; u++) {
+        const int cb = cb0 + u * kPeelThreads;
+        if (cb >= span) break;
+        const int bk = sbase + cb + tid;
+        int key = 0;
+        cplx val = make_double2(0.0, 0.0);
+        bool have = false;
+        if (cb + tid < span)
+          have = which == 0 ? decode_one_mansour(c, bk, s0[u], s1[u], key, val)
+                            : decode_one_gauss(c, which, bk, s0[u], s1[u], key, val);
+        if (have) { park_key[bk] = key; park_val[bk] = val; }
+        const unsigned bal = __ballot_sync(0xffffffffu, have);
+        if (lane == 0) sflags[(cb >> 5) + warp] = bal;
       }
     }
-    found = ordered_append(have, key, val, found, c.est_key, c.est_val, g.est_cap, warp_tot);
+    __syncthreads();
+    const int nwords = (span + 31) >> 5;
+    // each thread owns two consecutive flag words
+    const int w0 = 2 * tid;
+    const unsigned f0 = w0 < nwords ? sflags[w0] : 0u, f1 = w0 + 1 < nwords ? sflags[w0 + 1] : 0u;
+    int total;
+    int pos = found + block_scan_excl(__popc(f0) + __popc(f1), total, warp_tot);
+    unsigned bits = f0;
+    int wbase = sbase + w0 * 32;
+    for (int rep = 0; rep < 2; rep++) {
+      while (bits) {
+        const int bk = wbase + __ffs(bits) - 1;
+        bits &= bits - 1;
+        if (pos < g.est_cap) { c.est_key[pos] = park_key[bk]; c.est_val[pos] = park_val[bk]; }
+        pos++;
+      }
+      bits = f1;
+      wbase += 32;
+    }
+    found += total;
+    __syncthreads();
   }
   return found < g.est_cap ? found : g.est_cap;
 }
@@ -405,14 +459,24 @@ __device__ void mansour_targets(const PeelCtx &c, int key, cplx value, int *slot
 }
 
 // Subtract, from every touched bucket, the deltas of items [0, F) in item order.
-// keys/vals: the items; which groups to peel is given by the flags.
-// key_is_ans: keys are plain frequencies (UPDATE_ALL semantics); the permuted filter sees
-// (key*ai + shift) mod n   (:465-482, :944)
+// keys/vals: the items (plain frequencies; the permuted filter sees (key*ai + shift) mod n,
+// :465-482, :944); the flags say which filters to peel.
+// Deterministic whatever the thread timing: targets are counting-sorted by bucket (atomics
+// decide only the order INSIDE a segment), then one thread per touched bucket applies its
+// segment in ascending target id, i.e. in item order.
 __device__ void peel_apply(const PeelCtx &c, const int *keys, const cplx *vals, int F, bool do_g2,
-                           bool do_g1, bool do_man)
+                           bool do_g1, bool do_man, unsigned *warp_tot)
 {
+  __shared__ int ntouched;
   const V3Geom &g = c.g;
-  for (int i = threadIdx.x; i < F; i += kPeelThreads) {
+  const int tid = threadIdx.x;
+  int *cnt = c.head;                              // [nslots], zero between calls
+  int *fill = c.t_next;                           // [nslots] running fill pointers
+  int *touched = c.t_next + g.nslots;             // [nslots] buckets with at least one target
+  int *seg = c.t_next + 2 * g.nslots;             // [F*14] target ids grouped by bucket
+  if (tid == 0) ntouched = 0;
+  __syncthreads();
+  for (int i = tid; i < F; i += kPeelThreads) {
     const int key = keys[i];
     const cplx v = vals[i];
     int slots[14];
@@ -433,30 +497,45 @@ __device__ void peel_apply(const PeelCtx &c, const int *keys, const cplx *vals, 
       c.t_slot[t] = slots[q];
       if (slots[q] >= 0) {
         c.t_delta[t] = deltas[q];
-        c.t_next[t] = atomicExch(&c.head[slots[q]], t);
+        if (atomicAdd(&cnt[slots[q]], 1) == 0) touched[atomicAdd(&ntouched, 1)] = slots[q];
       }
     }
   }
   __syncthreads();
-  for (int t = threadIdx.x; t < F * 14; t += kPeelThreads) {
+  const int T = ntouched;
+  // segment starts: scan the counts of the touched buckets, a tile of 1024 at a time
+  int base = 0;
+  for (int j0 = 0; j0 < T; j0 += kPeelThreads) {
+    const int j = j0 + tid;
+    const int sl = j < T ? touched[j] : -1;
+    int total;
+    const int excl = block_scan_excl(sl >= 0 ? cnt[sl] : 0, total, warp_tot);
+    if (sl >= 0) fill[sl] = base + excl;
+    base += total;
+  }
+  __syncthreads();
+  for (int t = tid; t < F * 14; t += kPeelThreads) {
     const int slot = c.t_slot[t];
-    if (slot < 0 || c.head[slot] != t) continue;      // one leader per touched bucket
-    cplx val = c.samp[slot];
+    if (slot >= 0) seg[atomicAdd(&fill[slot], 1)] = t;
+  }
+  __syncthreads();
+  for (int j = tid; j < T; j += kPeelThreads) {
+    const int sl = touched[j];
+    const int len = cnt[sl];
+    const int *ids = seg + (fill[sl] - len);
+    cplx val = c.samp[sl];
     int last = -1;
-    for (;;) {                                         // ascending target id == item order
+    for (int rep = 0; rep < len; rep++) {          // ascending target id == item order
       int best = 0x7fffffff;
-      for (int id = t; id >= 0; id = c.t_next[id])
+      for (int q = 0; q < len; q++) {
+        const int id = ids[q];
         if (id > last && id < best) best = id;
-      if (best == 0x7fffffff) break;
+      }
       val = csub_rn(val, c.t_delta[best]);
       last = best;
     }
-    c.samp[slot] = val;
-  }
-  __syncthreads();
-  for (int t = threadIdx.x; t < F * 14; t += kPeelThreads) {
-    const int slot = c.t_slot[t];
-    if (slot >= 0) c.head[slot] = -1;
+    c.samp[sl] = val;
+    cnt[sl] = 0;
   }
   __syncthreads();
 }
@@ -526,22 +605,11 @@ __device__ int ans_accumulate(const PeelCtx &c, int F, int ans_count, bool assig
   return ans_count;
 }
 
-__device__ int block_count(bool flag, unsigned *warp_tot)
-{
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const unsigned bal = __ballot_sync(0xffffffffu, flag);
-  if (lane == 0) warp_tot[warp] = __popc(bal);
-  __syncthreads();
-  int tot = 0;
-  for (int w = 0; w < kPeelThreads / 32; w++) tot += (int)warp_tot[w];
-  __syncthreads();
-  return tot;
-}
-
 __global__ void __launch_bounds__(kPeelThreads)
 v3_peel_kernel(V3Geom g, PeelArgs a)
 {
-  __shared__ unsigned warp_tot[32];
+  __shared__ unsigned warp_tot[33];
+  __shared__ unsigned sflags[kFlagWords];
   const int s = blockIdx.x;
   PeelCtx c;
   c.g = g;
@@ -552,7 +620,7 @@ v3_peel_kernel(V3Geom g, PeelArgs a)
   c.est_key = a.est_key + (long long)s * g.est_cap;
   c.est_val = a.est_val + (long long)s * g.est_cap;
   c.t_slot = a.t_slot + (long long)s * g.tgt_cap * 14;
-  c.t_next = a.t_next + (long long)s * g.tgt_cap * 14;
+  c.t_next = a.t_next + (long long)s * (g.tgt_cap * 14 + 2 * g.nslots);
   c.t_delta = a.t_delta + (long long)s * g.tgt_cap * 14;
   c.hkey = a.hkey + (long long)s * g.hash_size;
   c.hidx = a.hidx + (long long)s * g.hash_size;
@@ -560,13 +628,17 @@ v3_peel_kernel(V3Geom g, PeelArgs a)
   c.ans_val = a.ans_val + (long long)s * g.ans_cap;
   c.fwin1 = a.fwin1; c.fwin2 = a.fwin2;
 
-  for (long long i = threadIdx.x; i < g.nslots; i += kPeelThreads) c.head[i] = -1;
+  for (long long i = threadIdx.x; i < g.nslots; i += kPeelThreads) c.head[i] = 0;
   for (int i = threadIdx.x; i < g.hash_size; i += kPeelThreads) c.hkey[i] = -1;
   __syncthreads();
 
+  long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  long long tmark = clock64();
+#define PROF(slot) { const long long now_ = clock64(); prof[slot] += now_ - tmark; tmark = now_; }
   int ans_count = 0;
   // ---- aliasing filter: decode, record, clear the decoded buckets (:842-855) ----
-  int F = decode_mansour(c, warp_tot);
+  int F = decode_filter(c, 0, warp_tot, sflags);
+  PROF(0)
   ans_count = ans_accumulate(c, F, ans_count, true, warp_tot, nullptr);
   for (int i = threadIdx.x; i < F; i += kPeelThreads) {
     // MAN_SAMP[j + 2*(f % W)] = 0 for j = 0,1: in the interleaved layout that is
@@ -582,55 +654,62 @@ v3_peel_kernel(V3Geom g, PeelArgs a)
     return;
   }
   // ---- first window: peel what is known, decode, peel from window 1 + aliasing (:881-924) ----
-  peel_apply(c, c.ans_key, c.ans_val, ans_count, false, true, false);
-  F = decode_gauss(c, 1, warp_tot);
+  PROF(2)
+  peel_apply(c, c.ans_key, c.ans_val, ans_count, false, true, false, warp_tot);
+  PROF(4)
+  F = decode_filter(c, 1, warp_tot, sflags);
+  PROF(1)
   ans_count = ans_accumulate(c, F, ans_count, false, warp_tot, nullptr);
-  peel_apply(c, c.est_key, c.est_val, F, false, true, true);
+  PROF(2)
+  peel_apply(c, c.est_key, c.est_val, F, false, true, true, warp_tot);
+  PROF(3)
   // ---- permuted window (:940-981) ----
-  peel_apply(c, c.ans_key, c.ans_val, ans_count, true, false, false);
-  F = decode_gauss(c, 2, warp_tot);
+  peel_apply(c, c.ans_key, c.ans_val, ans_count, true, false, false, warp_tot);
+  PROF(4)
+  F = decode_filter(c, 2, warp_tot, sflags);
+  PROF(1)
   ans_count = ans_accumulate(c, F, ans_count, false, warp_tot, nullptr);
-  peel_apply(c, c.est_key, c.est_val, F, true, true, true);
+  PROF(2)
+  peel_apply(c, c.est_key, c.est_val, F, true, true, true, warp_tot);
+  PROF(3)
   // ---- round robin until the occupied-bucket counts repeat (:991-1076) ----
   int prev_m = 0, prev_1 = 0, prev_2 = 0, rounds = 0;
   for (int nana = 0;; nana++) {
-    if (nana % 3 == 0) F = decode_mansour(c, warp_tot);
-    else F = decode_gauss(c, nana % 3 == 1 ? 1 : 2, warp_tot);
+    if (nana % 3 == 0) { F = decode_filter(c, 0, warp_tot, sflags); PROF(0) }
+    else { F = decode_filter(c, nana % 3 == 1 ? 1 : 2, warp_tot, sflags); PROF(1) }
     ans_count = ans_accumulate(c, F, ans_count, false, warp_tot, nullptr);
-    peel_apply(c, c.est_key, c.est_val, F, true, true, true);
+    PROF(2)
+    peel_apply(c, c.est_key, c.est_val, F, true, true, true, warp_tot);
+    PROF(3)
     rounds = nana + 1;
     if (nana % 3 == 2) {
-      int cm = 0, c1 = 0, c2 = 0;
       // the reference indexes its interleaved arrays with a plain j < B (:1047-1057):
       // entry j is (bucket j/2, shift j%2)
-      for (int base = 0; base < g.B1; base += kPeelThreads) {
-        const int j = base + threadIdx.x;
-        bool f = false;
-        if (j < g.B1) { const cplx v = c.samp[g1_base(g) + (j & 1) * g.B1 + (j >> 1)]; f = cabs2_rn(v) > 1e-6; }
-        c1 += block_count(f, warp_tot);
+      int l1 = 0, l2 = 0, lm = 0;
+      for (int j = threadIdx.x; j < g.B1; j += kPeelThreads)
+        l1 += cabs2_rn(c.samp[g1_base(g) + (j & 1) * g.B1 + (j >> 1)]) > 1e-6;
+      for (int j = threadIdx.x; j < g.B2; j += kPeelThreads)
+        l2 += cabs2_rn(c.samp[g2_base(g) + (j & 1) * g.B2 + (j >> 1)]) > 1e-6;
+#pragma unroll 8
+      for (int j = threadIdx.x; j < g.W; j += kPeelThreads) {
+        const cplx v = c.samp[man_base(g) + j];
+        const double r = v.x / (double)g.W, m = v.y / (double)g.W;
+        lm += __dadd_rn(__dmul_rn(r, r), __dmul_rn(m, m)) > 1e-6;
       }
-      for (int base = 0; base < g.B2; base += kPeelThreads) {
-        const int j = base + threadIdx.x;
-        bool f = false;
-        if (j < g.B2) { const cplx v = c.samp[g2_base(g) + (j & 1) * g.B2 + (j >> 1)]; f = cabs2_rn(v) > 1e-6; }
-        c2 += block_count(f, warp_tot);
-      }
-      for (int base = 0; base < g.W; base += kPeelThreads) {
-        const int j = base + threadIdx.x;
-        bool f = false;
-        if (j < g.W) {
-          const cplx v = c.samp[man_base(g) + j];
-          const double r = v.x / (double)g.W, m = v.y / (double)g.W;
-          f = __dadd_rn(__dmul_rn(r, r), __dmul_rn(m, m)) > 1e-6;
-        }
-        cm += block_count(f, warp_tot);
-      }
+      const int c1 = block_sum(l1, warp_tot), c2 = block_sum(l2, warp_tot), cm = block_sum(lm, warp_tot);
+      PROF(5)
       if (prev_m == cm && prev_1 == c1 && prev_2 == c2) break;
       prev_m = cm; prev_1 = c1; prev_2 = c2;
       if (nana > 3000) break;      // safety net; the reference has none
     }
   }
-  if (threadIdx.x == 0) { a.count[s] = ans_count; a.rounds[s] = rounds; }
+  if (threadIdx.x == 0) {
+    a.count[s] = ans_count;
+    a.rounds[s] = rounds;
+    if (a.prof)
+      for (int q = 0; q < 8; q++) a.prof[s * 8 + q] = prof[q];
+  }
+#undef PROF
 }
 
 }  // namespace
@@ -663,7 +742,7 @@ static void v3_free_scratch(PlanV3 &v)
   cudaFree(v.d_samp); cudaFree(v.d_head); cudaFree(v.d_est_key); cudaFree(v.d_est_val);
   cudaFree(v.d_t_slot); cudaFree(v.d_t_next); cudaFree(v.d_t_delta); cudaFree(v.d_hkey);
   cudaFree(v.d_hidx); cudaFree(v.d_ans_key); cudaFree(v.d_ans_val); cudaFree(v.d_count);
-  cudaFree(v.d_rounds); cudaFree(v.d_draw);
+  cudaFree(v.d_rounds); cudaFree(v.d_draw); cudaFree(v.d_prof); v.d_prof = nullptr;
   for (int i = 0; i < kStageSlots; i++) {
     if (v.h_draw[i]) cudaFreeHost(v.h_draw[i]);
     v.h_draw[i] = nullptr;
@@ -687,7 +766,7 @@ static int v3_ensure_capacity(PlanImpl *p, int nsig)
   SFFTB_CUDA(cudaMalloc(&v.d_est_key, sizeof(int) * S * v.est_cap));
   SFFTB_CUDA(cudaMalloc(&v.d_est_val, sizeof(cplx) * S * v.est_cap));
   SFFTB_CUDA(cudaMalloc(&v.d_t_slot, sizeof(int) * S * v.tgt_cap * 14));
-  SFFTB_CUDA(cudaMalloc(&v.d_t_next, sizeof(int) * S * v.tgt_cap * 14));
+  SFFTB_CUDA(cudaMalloc(&v.d_t_next, sizeof(int) * S * (v.tgt_cap * 14 + 2 * v.nslots)));
   SFFTB_CUDA(cudaMalloc(&v.d_t_delta, sizeof(cplx) * S * v.tgt_cap * 14));
   SFFTB_CUDA(cudaMalloc(&v.d_hkey, sizeof(int) * S * v.hash_size));
   SFFTB_CUDA(cudaMalloc(&v.d_hidx, sizeof(int) * S * v.hash_size));
@@ -696,6 +775,7 @@ static int v3_ensure_capacity(PlanImpl *p, int nsig)
   SFFTB_CUDA(cudaMalloc(&v.d_count, sizeof(int) * S));
   SFFTB_CUDA(cudaMalloc(&v.d_rounds, sizeof(int) * S));
   SFFTB_CUDA(cudaMalloc(&v.d_draw, sizeof(int) * S * D_INTS));
+  SFFTB_CUDA(cudaMalloc(&v.d_prof, sizeof(long long) * S * 8));
   for (int i = 0; i < kStageSlots; i++)
     SFFTB_CUDA(cudaHostAlloc(&v.h_draw[i], sizeof(int) * S * D_INTS, cudaHostAllocDefault));
   v.cap = nsig;
@@ -835,6 +915,7 @@ int v3_exec(PlanImpl *p, const cplx *d_in, long long stride, int nsig, const sff
   a.hkey = v.d_hkey; a.hidx = v.d_hidx; a.ans_key = v.d_ans_key; a.ans_val = v.d_ans_val;
   a.count = v.d_count; a.rounds = v.d_rounds;
   a.fwin1 = v.filt[0].fwin; a.fwin2 = v.filt[1].fwin;
+  a.prof = v.d_prof;
   v3_peel_kernel<<<nsig, kPeelThreads, 0, st>>>(g, a);
   SFFTB_LAUNCH_CHECK();
   timer_mark(p, "peel");
@@ -881,6 +962,7 @@ long long v3_debug_fetch(PlanImpl *p, const char *what, void *dst, size_t capaci
   else if (w == "gauss_samp") { src = v.d_samp + 2 * v.B_g2; bytes = sizeof(cplx) * 2ll * v.B_g1; }
   else if (w == "man_samp") { src = v.d_samp + 2 * v.B_g2 + 2 * v.B_g1; bytes = sizeof(cplx) * 2ll * v.W_Man; }
   else if (w == "rounds") { src = v.d_rounds; bytes = sizeof(int); }
+  else if (w == "peel_cycles") { src = v.d_prof; bytes = sizeof(long long) * 8; }
   else if (w == "twiddle") { src = v.d_tw; bytes = sizeof(cplx) * ((1ll << v.log_twN) - 1); }
   else { set_error("sfftb_debug_fetch: unknown v3 array name"); return -1; }
   if (bytes > (long long)capacity) { set_error("sfftb_debug_fetch: destination too small"); return -1; }
