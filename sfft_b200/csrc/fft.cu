@@ -73,16 +73,53 @@ constexpr int kLaterPassStages = 8;    // keeps >= 8 adjacent columns (128 B) pe
 // MODE 2: two-factor twiddles for large transforms, W_N^K = A[K >> 14] * F[K & 16383]
 //         (`tw` = A, `tw2` = F, N = 2^log_twN): the oracle's definition for N > 2^17
 template <int MODE>
+__device__ __forceinline__ cplx twiddle_at(int s, unsigned long long k, bool first_pass, const cplx *stw,
+                                           const cplx *__restrict__ tw, const cplx *__restrict__ tw2,
+                                           int log_twN, int sign)
+{
+  cplx w;
+  if (MODE == 1) {
+    w = first_pass ? stw[(1 << s) - 1 + (int)k] : __ldg(&tw[(1ull << s) - 1ull + k]);
+  } else if (MODE == 2) {
+    const unsigned long long K = k << (log_twN - s - 1);
+    w = cmul_rn(__ldg(&tw[K >> kTwFineLog]), __ldg(&tw2[K & ((1ull << kTwFineLog) - 1ull)]));
+  } else {
+    double sn, cs;
+    sincospi((double)k / (double)(1ull << s), &sn, &cs);
+    w = make_double2(cs, -sn);
+  }
+  if (sign > 0) w.y = -w.y;
+  return w;
+}
+
+__device__ __forceinline__ void butterfly(cplx &u, cplx &v, cplx w)
+{
+  const cplx t = cmul_rn(w, v);
+  const cplx a = u;
+  u = cadd_rn(a, t);
+  v = csub_rn(a, t);
+}
+
+// The first pass works on one contiguous run of points: its threads read 8 neighbours
+// each, which would land on the same banks; one pad slot per 8 points spreads them.
+__device__ __forceinline__ int tile_slot(int i, bool padded) { return padded ? i + (i >> 3) : i; }
+
+// Each round takes up to three consecutive stages of the radix-2 graph in registers:
+// a thread owns the 8 points that differ in the three stage bits, so the arithmetic (and
+// its rounding) is exactly the radix-2 butterflies, with a third of the barriers and
+// shared-memory traffic.
+template <int MODE>
 __global__ void __launch_bounds__(kFftThreads)
 fft_pass_kernel(cplx *base, int s0, int ns, int logT, long long fft_stride,
                 long long sig_stride, const cplx *__restrict__ tw, const cplx *__restrict__ tw2,
                 int log_twN, int sign)
 {
-  constexpr bool TABLE = MODE == 1;
   extern __shared__ cplx tile[];
-  cplx *stw = tile + (1 << (ns + logT));      // only used when TABLE && s0 == 0
+  const bool first_pass = s0 == 0;
+  const bool padded = logT == 0;
   const int T = 1 << logT;
   const int elems = 1 << (ns + logT);
+  cplx *stw = tile + tile_slot(elems, padded) + 1;      // only used when MODE == 1 && first_pass
   const int lhi_bits = s0 - logT;
   const unsigned tile_id = blockIdx.x;
   const unsigned Lhi = tile_id & ((1u << lhi_bits) - 1u);
@@ -93,47 +130,65 @@ fft_pass_kernel(cplx *base, int s0, int ns, int logT, long long fft_stride,
 
   for (int e = threadIdx.x; e < elems; e += kFftThreads) {
     const int r = e >> logT, c = e & (T - 1);
-    tile[e] = fft[base_idx + ((unsigned long long)r << s0) + c];
+    tile[tile_slot(e, padded)] = fft[base_idx + ((unsigned long long)r << s0) + c];
   }
-  if (TABLE && s0 == 0)
+  if (MODE == 1 && first_pass)
     for (int e = threadIdx.x; e < (1 << ns) - 1; e += kFftThreads) stw[e] = __ldg(&tw[e]);
   __syncthreads();
 
   const unsigned long long Lfixed = (unsigned long long)Lhi << logT;
-  for (int st = 0; st < ns; st++) {
-    const int s = s0 + st;
-    for (int q = threadIdx.x; q < elems / 2; q += kFftThreads) {
-      const int c = q & (T - 1);
-      const int rr = q >> logT;
-      const int r_lo = rr & ((1 << st) - 1);
-      const int r_hi = rr >> st;
-      const int r0 = (r_hi << (st + 1)) | r_lo;
-      const int r1 = r0 | (1 << st);
-      const unsigned long long k = ((unsigned long long)r_lo << s0) | Lfixed | (unsigned)c;
-      cplx w;
-      if (TABLE) {
-        w = s0 == 0 ? stw[(1 << s) - 1 + (int)k] : __ldg(&tw[(1ull << s) - 1ull + k]);
-      } else if (MODE == 2) {
-        const unsigned long long K = k << (log_twN - s - 1);
-        w = cmul_rn(__ldg(&tw[K >> kTwFineLog]), __ldg(&tw2[K & ((1ull << kTwFineLog) - 1ull)]));
-      } else {
-        double sn, cs;
-        sincospi((double)k / (double)(1ull << s), &sn, &cs);
-        w = make_double2(cs, -sn);
+  int st = 0;
+  while (st < ns) {
+    const int r = ns - st >= 3 ? 3 : ns - st;          // stages this round
+    const int units = elems >> r;
+    for (int u = threadIdx.x; u < units; u += kFftThreads) {
+      const int c = u & (T - 1);
+      const int ru = u >> logT;
+      const int r_lo = ru & ((1 << st) - 1);
+      const int r_hi = ru >> st;
+      const int row0 = (r_hi << (st + r)) | r_lo;
+      const unsigned long long kbase = ((unsigned long long)r_lo << s0) | Lfixed | (unsigned)c;
+      const unsigned long long kstep = 1ull << (s0 + st);
+      cplx v[8];
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        if (j < (1 << r)) v[j] = tile[tile_slot(((row0 + (j << st)) << logT) | c, padded)];
+      // stage s0+st: pairs (j, j+1)
+      {
+        const cplx w = twiddle_at<MODE>(s0 + st, kbase, first_pass, stw, tw, tw2, log_twN, sign);
+#pragma unroll
+        for (int j = 0; j < 8; j += 2)
+          if (j < (1 << r)) butterfly(v[j], v[j + 1], w);
       }
-      if (sign > 0) w.y = -w.y;
-      const int i0 = (r0 << logT) | c, i1 = (r1 << logT) | c;
-      const cplx u = tile[i0], v = tile[i1];
-      const cplx t = cmul_rn(w, v);
-      tile[i0] = cadd_rn(u, t);
-      tile[i1] = csub_rn(u, t);
+      if (r >= 2) {   // stage s0+st+1: pairs (j, j+2)
+        const cplx w0 = twiddle_at<MODE>(s0 + st + 1, kbase, first_pass, stw, tw, tw2, log_twN, sign);
+        const cplx w1 = twiddle_at<MODE>(s0 + st + 1, kbase + kstep, first_pass, stw, tw, tw2, log_twN, sign);
+#pragma unroll
+        for (int j = 0; j < 8; j += 4)
+          if (j < (1 << r)) {
+            butterfly(v[j], v[j + 2], w0);
+            butterfly(v[j + 1], v[j + 3], w1);
+          }
+      }
+      if (r >= 3) {   // stage s0+st+2: pairs (j, j+4)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const cplx w = twiddle_at<MODE>(s0 + st + 2, kbase + (unsigned long long)j * kstep, first_pass, stw, tw,
+                                          tw2, log_twN, sign);
+          butterfly(v[j], v[j + 4], w);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; j++)
+        if (j < (1 << r)) tile[tile_slot(((row0 + (j << st)) << logT) | c, padded)] = v[j];
     }
     __syncthreads();
+    st += r;
   }
 
   for (int e = threadIdx.x; e < elems; e += kFftThreads) {
     const int r = e >> logT, c = e & (T - 1);
-    fft[base_idx + ((unsigned long long)r << s0) + c] = tile[e];
+    fft[base_idx + ((unsigned long long)r << s0) + c] = tile[tile_slot(e, padded)];
   }
 }
 
@@ -171,12 +226,15 @@ int fft_dit_inplace_ex(cplx *base, int logN, int nfft, long long fft_stride, int
     }
     const long long tiles = 1ll << (logN - ns - logT);
     dim3 grid((unsigned)tiles, (unsigned)nfft, (unsigned)nsig);
-    size_t smem = sizeof(cplx) << (ns + logT);
+    const size_t tile_elems = (size_t)1 << (ns + logT);
+    size_t smem = sizeof(cplx) * (tile_elems + (logT == 0 ? (tile_elems >> 3) : 0) + 2);
     if (tw && !tw_fine && s0 == 0) smem += sizeof(cplx) << ns;
     static bool attr_set = false;
     if (!attr_set) {
-      SFFTB_CUDA(cudaFuncSetAttribute(fft_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                      (int)(2 * (sizeof(cplx) << kMaxTileLog))));
+      const int max_smem = (int)(sizeof(cplx) * ((2u << kMaxTileLog) + (1u << (kMaxTileLog - 3)) + 4));
+      SFFTB_CUDA(cudaFuncSetAttribute(fft_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+      SFFTB_CUDA(cudaFuncSetAttribute(fft_pass_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
+      SFFTB_CUDA(cudaFuncSetAttribute(fft_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
       attr_set = true;
     }
     if (tw && tw_fine)
