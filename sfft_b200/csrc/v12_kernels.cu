@@ -102,6 +102,7 @@ int launch_gather(const LoopGeom &g, const GatherArgs &a, int nloops, int nsig, 
 // ---------------------------------------------------------------------------
 constexpr int kSelectThreads = 1024;
 constexpr int kSelectSmemKeys = 16384;   // rows up to this size keep their keys in shared memory
+constexpr int kSelectCand = 1024;        // survivors of the radix passes finished from a compact list
 
 __device__ __forceinline__ int key_slot(int i, bool padded) { return padded ? i + (i >> 4) : i; }
 
@@ -112,7 +113,8 @@ select_kernel(SelectArgs a)
   __shared__ unsigned hist[256];
   __shared__ unsigned long long warp_tot[32];
   __shared__ unsigned long long sh_prefix;
-  __shared__ unsigned sh_K;
+  __shared__ unsigned sh_K, sh_bin, sh_ncand;
+  __shared__ unsigned long long cand[kSelectCand];
 
   const int row = a.row_begin + blockIdx.x * a.row_step;
   const int s = blockIdx.y;
@@ -139,29 +141,36 @@ select_kernel(SelectArgs a)
 
   unsigned long long prefix = 0;
   unsigned K = (unsigned)a.num + 1u;      // rank from the top of the wanted key
+  bool compacted = false;                 // block-uniform
   for (int pass = 0; pass < 8; pass++) {
     const int shift = 56 - 8 * pass;
     if (tid < 256) hist[tid] = 0;
     __syncthreads();
-    int run_d = -1;
-    unsigned run_c = 0;
-    for (int e = 0; e < mine; e++) {
-      // the histogram does not care which keys a thread counts: shared-memory keys are
-      // read chunk-wise (padded, conflict-free), global ones strided so warps coalesce
-      const unsigned long long key = in_smem ? keys[key_slot(lo + e, true)] : keys[e * kSelectThreads + tid];
-      const bool match = pass == 0 ? true : ((key >> (shift + 8)) == prefix);
-      if (match) {
-        const int d = (int)((key >> shift) & 255ull);
-        if (d == run_d) {
-          run_c++;
-        } else {
-          if (run_c) atomicAdd(&hist[run_d], run_c);
-          run_d = d;
-          run_c = 1;
+    if (!compacted) {
+      int run_d = -1;
+      unsigned run_c = 0;
+      for (int e = 0; e < mine; e++) {
+        // the histogram does not care which keys a thread counts: shared-memory keys are
+        // read chunk-wise (padded, conflict-free), global ones strided so warps coalesce
+        const unsigned long long key = in_smem ? keys[key_slot(lo + e, true)] : keys[e * kSelectThreads + tid];
+        const bool match = pass == 0 ? true : ((key >> (shift + 8)) == prefix);
+        if (match) {
+          const int d = (int)((key >> shift) & 255ull);
+          if (d == run_d) {
+            run_c++;
+          } else {
+            if (run_c) atomicAdd(&hist[run_d], run_c);
+            run_d = d;
+            run_c = 1;
+          }
         }
       }
+      if (run_c) atomicAdd(&hist[run_d], run_c);
+    } else if (tid < (int)sh_ncand) {
+      // few keys still share the prefix: they were copied out, one per thread
+      const unsigned long long key = cand[tid];
+      if ((key >> (shift + 8)) == prefix) atomicAdd(&hist[(int)((key >> shift) & 255ull)], 1u);
     }
-    if (run_c) atomicAdd(&hist[run_d], run_c);
     __syncthreads();
     if (warp == 0) {
       // lane l owns bins 255-8l .. 248-8l, i.e. lanes ascend as keys descend
@@ -185,6 +194,7 @@ select_kernel(SelectArgs a)
           if (K <= run + c8[q]) {
             sh_prefix = (prefix << 8) | (unsigned long long)(255 - 8 * lane - q);
             sh_K = K - run;
+            sh_bin = c8[q];
             break;
           }
           run += c8[q];
@@ -194,6 +204,17 @@ select_kernel(SelectArgs a)
     __syncthreads();
     prefix = sh_prefix;
     K = sh_K;
+    // once at most kSelectCand keys share the decided prefix, gather them and finish on those
+    if (!compacted && pass < 7 && sh_bin <= (unsigned)kSelectCand) {
+      if (tid == 0) sh_ncand = 0;
+      __syncthreads();
+      for (int e = 0; e < mine; e++) {
+        const unsigned long long key = in_smem ? keys[key_slot(lo + e, true)] : keys[e * kSelectThreads + tid];
+        if ((key >> shift) == prefix) cand[atomicAdd(&sh_ncand, 1u)] = key;
+      }
+      compacted = true;
+      __syncthreads();
+    }
   }
   const unsigned long long cutoff = prefix;
   const unsigned need = K - 1u;   // ties at the cutoff to admit, in index order
@@ -328,7 +349,10 @@ vote_kernel(LoopGeom g, VoteArgs a, long long total_per_sig)
       if (voted_by(g, a, s, jj, loc)) { earlier = true; break; }
     if (earlier) continue;
     int score = 1;
-    for (int jj = j + 1; jj < g.loops_loc; jj++) score += voted_by(g, a, s, jj, loc) ? 1 : 0;
+    for (int jj = j + 1; jj < g.loops_loc; jj++) {
+      if (score + (g.loops_loc - jj) < a.thresh) break;      // cannot reach the threshold any more
+      score += voted_by(g, a, s, jj, loc) ? 1 : 0;
+    }
     if (score >= a.thresh) {
       const int pos = atomicAdd(&a.count[s], 1);
       if (pos < a.hits_cap) a.hits[(long long)s * a.hits_cap + pos] = (int)loc;
