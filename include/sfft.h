@@ -157,6 +157,9 @@ int sfftb_exec_many_device(sfft_plan *plan, int num, const void *d_in,
 /* Zero d_out[0..n) and scatter the sparse result of signal `which` into it (device). */
 int sfftb_densify(sfft_plan *plan, int which, void *d_out);
 
+/* Wait until everything queued on the plan's stream has finished. */
+int sfftb_synchronize(sfft_plan *plan);
+
 /* Copy the sparse result of signal `which` to host arrays (capacity entries). */
 long long sfftb_fetch_result(sfft_plan *plan, int which, int *loc, sfft_complex *val,
                              long long capacity);

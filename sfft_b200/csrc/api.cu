@@ -352,6 +352,15 @@ int sfftb_densify(sfft_plan *plan, int which, void *d_out)
   return launch_scatter(loc, val, cnt, (cplx *)d_out, p->stream);
 }
 
+int sfftb_synchronize(sfft_plan *plan)
+{
+  PlanImpl *p = impl(plan);
+  if (!p) { set_error("sfftb_synchronize: null plan"); return -1; }
+  if (bind_device(p)) return -1;
+  SFFTB_CUDA(cudaStreamSynchronize(p->stream));
+  return 0;
+}
+
 long long sfftb_fetch_result(sfft_plan *plan, int which, int *loc_out, sfft_complex *val_out,
                              long long capacity)
 {

@@ -152,11 +152,19 @@ class sfft:
                 raise RuntimeError(_lib.last_error())
         return loc, val
 
-    def densify(self, out, which=0):
-        """Zero `out` (CUDA tensor complex128[n]) and scatter the sparse result."""
+    def densify(self, out, which=0, sync=True):
+        """Zero `out` (CUDA tensor complex128[n]) and scatter the sparse result.  The work is
+        queued on the plan's stream; sync=True waits for it (needed unless the caller's own
+        work runs on that same stream, see set_stream)."""
         if self._L.sfftb_densify(self.sfft_plan, which, C.c_void_p(out.data_ptr())):
             raise RuntimeError(_lib.last_error())
+        if sync:
+            self.synchronize()
         return out
+
+    def synchronize(self):
+        if self._L.sfftb_synchronize(self.sfft_plan):
+            raise RuntimeError(_lib.last_error())
 
     def debug_fetch(self, what, dtype, count):
         buf = np.empty(count, dtype=dtype)
