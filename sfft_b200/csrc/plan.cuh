@@ -59,7 +59,7 @@ struct PlanV12 {
   unsigned *d_appr_bm = nullptr;   // [cap][W/32]
   int *d_approved = nullptr;       // [cap][W]
   int *d_num_comb = nullptr;       // [cap]
-  cplx *d_V = nullptr;             // v2 structured estimation: [loops][max_comb][n/W] (single signal)
+  cplx *d_xt = nullptr;            // v2 structured estimation: class-major copy of d_xs
   int max_comb = 0;
   // per-transform draws: a[loops], ai[loops] per signal, then comb offsets
   int *d_stage = nullptr;          // [cap * ints_per_sig]

@@ -201,7 +201,7 @@ static void v12_free_scratch(PlanV12 &v)
   cudaFree(v.d_voted); cudaFree(v.d_voted_count); cudaFree(v.d_hit_loc); cudaFree(v.d_hit_val);
   cudaFree(v.d_count); cudaFree(v.d_comb_xs); cudaFree(v.d_comb_J); cudaFree(v.d_comb_bm);
   cudaFree(v.d_appr_bm); cudaFree(v.d_approved); cudaFree(v.d_num_comb); cudaFree(v.d_stage);
-  cudaFree(v.d_V); v.d_V = nullptr;
+  cudaFree(v.d_xt); v.d_xt = nullptr;
   for (int i = 0; i < kStageSlots; i++) {
     if (v.h_stage[i]) cudaFreeHost(v.h_stage[i]);
     v.h_stage[i] = nullptr;
@@ -245,13 +245,8 @@ int v12_ensure_capacity(PlanImpl *p, int nsig)
     SFFTB_CUDA(cudaMalloc(&v.d_num_comb, sizeof(int) * S));
     if (W > 16384 && (long long)v.Comb_loops * W > gk) gk = (long long)v.Comb_loops * W;
     v.max_comb = (int)((long long)v.Comb_loops * num < W ? (long long)v.Comb_loops * num : W);
-    if (nsig == 1 && v2_struct_supported(v.geom, ilog2((unsigned)W)) && !getenv("SFFTB_NO_V2_STRUCT")) {
-      // a failed allocation just leaves the generic estimator in charge
-      if (cudaMalloc(&v.d_V, sizeof(cplx) * (long long)v.geom.loops * v.max_comb * (p->n / W)) != cudaSuccess) {
-        cudaGetLastError();
-        v.d_V = nullptr;
-      }
-    }
+    if (v2_struct_supported(v.geom, ilog2((unsigned)W)) && !getenv("SFFTB_NO_V2_STRUCT"))
+      SFFTB_CUDA(cudaMalloc(&v.d_xt, sizeof(cplx) * S * v.x_samp_size));
   }
   v.gkeys_per_sig = gk;
   if (gk) SFFTB_CUDA(cudaMalloc(&v.d_gkeys, sizeof(unsigned long long) * S * gk));
@@ -441,18 +436,18 @@ static int v12_stage_finish(PlanImpl *p, int nsig, int slice_rank, int slice_wor
   ea.slice_rank = slice ? slice_rank : 0;
   ea.slice_world = slice ? slice_world : 1;
   ea.slice_count = slice ? v.d_count : nullptr;
-  if (v.with_comb && nsig == 1 && v.d_V) {
+  if (v.with_comb && v.d_xt) {
     V2StructArgs sa2;
-    sa2.perm = d_perm; sa2.xs = v.d_xs;
+    sa2.perm = d_perm; sa2.xs = v.d_xs; sa2.xt = v.d_xt;
     sa2.fwin[0] = ea.fwin[0]; sa2.fwin[1] = ea.fwin[1];
     sa2.fw_half[0] = ea.fw_half[0]; sa2.fw_half[1] = ea.fw_half[1];
     sa2.fdr[0] = ea.fdr[0]; sa2.fdr[1] = ea.fdr[1];
-    sa2.approved = v.d_approved; sa2.num_comb = v.d_num_comb;
+    sa2.approved = v.d_approved; sa2.approved_stride = v.W_Comb; sa2.num_comb = v.d_num_comb;
     sa2.logW = ilog2((unsigned)v.W_Comb);
-    sa2.V = v.d_V;
+    sa2.logT = v2_struct_log_tile(g, sa2.logW);
     sa2.out_loc = v.d_hit_loc; sa2.out_val = v.d_hit_val; sa2.out_cap = v.max_hits;
     sa2.slice_rank = ea.slice_rank; sa2.slice_world = ea.slice_world; sa2.slice_count = ea.slice_count;
-    if (launch_v2_struct(g, sa2, v.max_comb, st)) return -1;
+    if (launch_v2_struct(g, sa2, v.max_comb, nsig, st)) return -1;
   } else {
     if (launch_estimate(g, ea, nsig, v.max_hits, st)) return -1;
   }

@@ -652,8 +652,7 @@ int launch_estimate(const LoopGeom &g, const EstimateArgs &a, int nsig, long lon
 // ---------------------------------------------------------------------------
 // v2 structured estimation (see v12_kernels.cuh)
 // ---------------------------------------------------------------------------
-constexpr int kV2Threads = 1024;
-constexpr int kV2Chunks = 8;          // residue chunks per (loop, class)
+constexpr int kV2LogTile = 8;         // hits per tile = threads per CTA (at most)
 
 __device__ __forceinline__ void v2_slice(const V2StructArgs &a, long long total, long long &lo, long long &hi)
 {
@@ -664,87 +663,207 @@ __device__ __forceinline__ void v2_slice(const V2StructArgs &a, long long total,
   }
 }
 
-__global__ void __launch_bounds__(kV2Threads)
-v2_values_kernel(LoopGeom g, V2StructArgs a)
+// class-major copy of every bucket spectrum: xt[(b mod 2^t) * T + (b >> t)] = xs[b],
+// T = 2^logT, t = logB - logT.  Buckets that agree modulo 2^t become contiguous.
+__global__ void v2_regroup_kernel(LoopGeom g, const cplx *__restrict__ xs, cplx *__restrict__ xt,
+                                  int logT)
 {
-  extern __shared__ cplx subrow[];
-  const int j = blockIdx.z, cls = blockIdx.y, chunk = blockIdx.x;
-  const bool est = j >= g.loops_loc;
-  const int logB = est ? g.logB[1] : g.logB[0];
-  const int logseg = g.logn - logB;
-  const int logq = a.logW - logseg;            // q = W / seg buckets per W positions
-  if (cls >= (1 << logq)) return;
-  const int logNW = g.logn - a.logW;           // n/W = buckets per class
-  const int NW = 1 << logNW;
-  const int nc = a.num_comb[0];
-  long long lo, hi;
-  v2_slice(a, (long long)nc * NW, lo, hi);
-  if (hi <= lo) return;
-  const int i_first = (int)(lo >> logNW), i_last = (int)((hi - 1) >> logNW);   // residues this launch needs
-  const int span = i_last - i_first + 1;
-  const int i0 = i_first + (int)((long long)span * chunk / kV2Chunks);
-  const int i1 = i_first + (int)((long long)span * (chunk + 1) / kV2Chunks);
-  if (i1 <= i0) return;
-
-  const cplx *__restrict__ row = a.xs + loop_offset(g, j);
-  for (int t = threadIdx.x; t < NW; t += kV2Threads) subrow[t] = row[cls + (t << logq)];
-  __syncthreads();
-
-  const unsigned mask = (unsigned)g.n_mask;
-  const unsigned ai = (unsigned)a.perm[g.loops + j];
-  const unsigned m = ai & (unsigned)(NW - 1);                // ai*W mod n = W * (ai mod n/W)
-  const int seg = 1 << logseg;
-  const cplx *__restrict__ fw = est ? a.fwin[1] : a.fwin[0];
-  const double2 *__restrict__ fdr = est ? a.fdr[1] : a.fdr[0];
-  const int half = est ? a.fw_half[1] : a.fw_half[0];
-  for (int i = i0; i < i1; i++) {
-    const unsigned r = (unsigned)__ldg(&a.approved[i]);
-    const unsigned pos = (unsigned)(((unsigned long long)ai * r) & mask);          // jj = 0
-    unsigned bucket = pos >> logseg;
-    int dist = (int)(pos & (unsigned)(seg - 1));
-    if (dist > seg / 2) {                                                           // cf12.cc:373-377
-      bucket = (bucket + 1) & ((1u << logB) - 1u);
-      dist -= seg;
-    }
-    if ((int)(bucket & ((1u << logq) - 1u)) != cls) continue;                       // other class's CTA
-    const unsigned t0 = bucket >> logq;
-    const cplx f = __ldg(&fw[half - dist]);
-    const double2 dr = __ldg(&fdr[half - dist]);
-    cplx *__restrict__ dst = a.V + (((long long)j * nc + i) << logNW);
-    for (int jj = threadIdx.x; jj < NW; jj += kV2Threads) {
-      const cplx sv = subrow[(t0 + m * (unsigned)jj) & (unsigned)(NW - 1)];
-      const double ac = __dmul_rn(sv.x, f.x), bd = __dmul_rn(sv.y, f.y);
-      const double ad = __dmul_rn(sv.x, f.y), bc = __dmul_rn(sv.y, f.x);
-      dst[jj] = make_double2(div_by_rcp_rn(__dadd_rn(ac, bd), dr.x, dr.y),
-                             div_by_rcp_rn(__dsub_rn(ad, bc), dr.x, dr.y));       // :388-398
-    }
-  }
+  const int j = blockIdx.y;
+  const long long sig = (long long)blockIdx.z * g.x_samp_size;
+  const int logB = j >= g.loops_loc ? g.logB[1] : g.logB[0];
+  const int t = logB - logT;
+  const unsigned o = blockIdx.x * blockDim.x + threadIdx.x;
+  if (o >= (1u << logB)) return;
+  const unsigned b = (o >> logT) | ((o & ((1u << logT) - 1u)) << t);
+  const long long off = sig + loop_offset(g, j);
+  xt[off + o] = xs[off + b];
 }
 
-template <int L>
-__global__ void __launch_bounds__(256, 2)
-v2_median_kernel(LoopGeom g, V2StructArgs a)
+// per-(tile, loop) constants, split so that every access is one aligned vector load
+struct V2TileParams {
+  cplx f[32];          // filter response at this residue's in-bucket offset
+  double2 dr[32];      // (|f|^2, RN(1/|f|^2))
+  uint2 pm[32];        // element of hit u: (pm.x + pm.y*u) mod T
+  unsigned r;          // the tile's residue
+  int den_unsafe;      // some |f|^2 outside div_fast's exponent band (sticky)
+};
+
+// a / b with y = RN(1/b): as div_by_rcp_rn without the guard; the caller checks the
+// exponents of every numerator once per hit and redoes the hit with real divisions
+// when one falls outside the band (exact zeros, in practice).
+__device__ __forceinline__ double div_fast(double a, double b, double y)
 {
+  double q = __dmul_rn(a, y);
+  double r = __fma_rn(-b, q, a);
+  q = __fma_rn(r, y, q);
+  r = __fma_rn(-b, q, a);
+  return __fma_rn(r, y, q);
+}
+
+__device__ __forceinline__ cplx lds_cplx(unsigned addr)
+{
+  cplx r;
+  asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "r"(addr));
+  return r;
+}
+__device__ __forceinline__ void mbar_init(unsigned bar, unsigned count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(unsigned bar, unsigned bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned bar, unsigned parity)
+{
+  unsigned done;
+  do {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(done) : "r"(bar), "r"(parity) : "memory");
+  } while (!done);
+}
+// one contiguous global -> shared copy by the TMA engine, completion counted on `bar`
+__device__ __forceinline__ void bulk_copy_g2s(unsigned dst, const void *src, unsigned bytes, unsigned bar)
+{
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+
+// Tile = (residue i, jj mod 2^s == c): T = (n/W)/2^s hits, one per thread.  In loop j those
+// hits read T buckets that agree modulo q*2^s -- one contiguous 16*T-byte run of xt -- so
+// L bulk copies bring the tile's inputs into shared memory; each thread picks its L values,
+// divides by the filter response, keeps the 2L quotients in registers and takes the two
+// medians.  No intermediate leaves the SM.  CTAs are persistent over a contiguous range of
+// tiles: while the medians of tile t run, the copies for tile t+1 are already in flight
+// (issued by the L parameter threads right after the last read of tile t's inputs), and
+// the per-residue constants are only reloaded when the residue changes.
+template <int L>
+__global__ void __launch_bounds__(1 << kV2LogTile, 512 >> kV2LogTile)
+v2_fused_kernel(LoopGeom g, V2StructArgs a)
+{
+  constexpr int logT = kV2LogTile, T = 1 << logT;
+  constexpr unsigned kRunBytes = T * sizeof(cplx);
+  extern __shared__ __align__(128) cplx v2_stage[];              // [L][T]
+  __shared__ V2TileParams prm;
+  __shared__ __align__(8) unsigned long long full_bar;
+  const int sig = blockIdx.y;
   const int logNW = g.logn - a.logW;
-  const int nc = a.num_comb[0];
+  const int sbits = logNW - logT;
+  const int nc = a.num_comb[sig];
   long long lo, hi;
-  v2_slice(a, (long long)nc << logNW, lo, hi);
-  if (a.slice_count && blockIdx.x == 0 && threadIdx.x == 0) a.slice_count[0] = (int)(hi - lo);
-  for (long long idx = lo + blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < hi;
-       idx += (long long)gridDim.x * blockDim.x) {
-    const int i = (int)(idx >> logNW);
-    const unsigned jj = (unsigned)(idx & ((1ll << logNW) - 1));
+  v2_slice(a, (long long)nc << sbits, lo, hi);
+  if (a.slice_count && blockIdx.x == 0 && threadIdx.x == 0) a.slice_count[0] = (int)((hi - lo) << logT);
+  const long long t_begin = lo + (hi - lo) * blockIdx.x / gridDim.x;
+  const long long t_end = lo + (hi - lo) * (blockIdx.x + 1) / gridDim.x;
+  if (t_begin >= t_end) return;
+  const unsigned u = threadIdx.x;
+  const unsigned stage0 = (unsigned)__cvta_generic_to_shared(v2_stage);
+  const unsigned bar = (unsigned)__cvta_generic_to_shared(&full_bar);
+  const cplx *__restrict__ xt = a.xt + (long long)sig * g.x_samp_size;
+
+  if (u == 0) {
+    mbar_init(bar, L);
+    prm.den_unsafe = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+
+  // ---- parameter threads: loop j = u ----
+  const bool is_param = u < (unsigned)L;
+  const int pj = is_param ? (int)u : 0;
+  const bool p_est = pj >= g.loops_loc;
+  const int p_logB = p_est ? g.logB[1] : g.logB[0];
+  const int p_logseg = g.logn - p_logB;
+  const int p_logq = a.logW - p_logseg;
+  const unsigned p_ai = (unsigned)a.perm[(long long)sig * perm_stride(g.loops) + g.loops + pj];
+  const unsigned p_m = p_ai & (unsigned)((1 << logNW) - 1);      // ai*W mod n = W * (ai mod n/W)
+  const unsigned p_off = (unsigned)loop_offset(g, pj);
+  int p_i = -1;
+  unsigned p_bucket = 0;
+  auto issue_tile = [&](long long tile) {
+    const int i = (int)(tile >> sbits);
+    const unsigned c = (unsigned)(tile & ((1ll << sbits) - 1));
+    if (i != p_i) {
+      p_i = i;
+      const unsigned r = (unsigned)__ldg(&a.approved[(long long)sig * a.approved_stride + i]);
+      const int seg = 1 << p_logseg;
+      const unsigned pos = (unsigned)(((unsigned long long)p_ai * r) & (unsigned)g.n_mask);   // jj = 0
+      unsigned bucket = pos >> p_logseg;
+      int dist = (int)(pos & (unsigned)(seg - 1));
+      if (dist > seg / 2) {                                                                 // cf12.cc:373-377
+        bucket = (bucket + 1) & ((1u << p_logB) - 1u);
+        dist -= seg;
+      }
+      p_bucket = bucket;
+      const int half = p_est ? a.fw_half[1] : a.fw_half[0];
+      const double2 dr = __ldg(&(p_est ? a.fdr[1] : a.fdr[0])[half - dist]);
+      prm.f[pj] = __ldg(&(p_est ? a.fwin[1] : a.fwin[0])[half - dist]);
+      prm.dr[pj] = dr;
+      if (pj == 0) prm.r = r;
+      const unsigned eb = ((unsigned)__double2hiint(dr.x) >> 20) & 0x7ffu;
+      if (eb - 640u >= 768u) prm.den_unsafe = 1;
+    }
+    const unsigned cls = p_bucket & ((1u << p_logq) - 1u);
+    const unsigned P = ((p_bucket >> p_logq) + p_m * c) & (unsigned)((1 << logNW) - 1);
+    const unsigned beta = cls | ((P & ((1u << sbits) - 1u)) << p_logq);
+    prm.pm[pj] = make_uint2((P >> sbits) & (unsigned)(T - 1), p_m & (unsigned)(T - 1));
+    // the CTA's reads of the previous tile (generic proxy) precede this copy (async proxy)
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    mbar_arrive_expect_tx(bar, kRunBytes);
+    bulk_copy_g2s(stage0 + (unsigned)pj * kRunBytes, xt + p_off + (beta << logT), kRunBytes, bar);
+  };
+  if (is_param) issue_tile(t_begin);
+
+  unsigned parity = 0;
+  for (long long tile = t_begin; tile < t_end; tile++) {
+    mbar_wait(bar, parity);
+    parity ^= 1u;
+    const unsigned r = prm.r;
     double vr[L], vi[L];
+    unsigned emin = 0x7fffffffu, emax = 0u;
 #pragma unroll
     for (int j = 0; j < L; j++) {
-      const cplx v = a.V[(((long long)j * nc + i) << logNW) + jj];
-      vr[j] = v.x;
-      vi[j] = v.y;
+      const uint2 pm = prm.pm[j];
+      const cplx f = prm.f[j];
+      const double2 dr = prm.dr[j];
+      const cplx sv = lds_cplx(stage0 + (unsigned)j * kRunBytes + (((pm.x + pm.y * u) & (unsigned)(T - 1)) << 4));
+      const double ac = __dmul_rn(sv.x, f.x), bd = __dmul_rn(sv.y, f.y);
+      const double ad = __dmul_rn(sv.x, f.y), bc = __dmul_rn(sv.y, f.x);
+      const double nr = __dadd_rn(ac, bd), ni = __dsub_rn(ad, bc);                  // :388-398
+      const unsigned hr = (unsigned)__double2hiint(nr) & 0x7fffffffu;
+      const unsigned hi2 = (unsigned)__double2hiint(ni) & 0x7fffffffu;
+      emin = min(emin, min(hr, hi2));
+      emax = max(emax, max(hr, hi2));
+      vr[j] = div_fast(nr, dr.x, dr.y);
+      vi[j] = div_fast(ni, dr.x, dr.y);
     }
+    if (emin < (640u << 20) || emax >= (1408u << 20) || prm.den_unsafe) {
+      // a numerator (or denominator) outside the band where div_fast is proven: redo exactly
+#pragma unroll 1
+      for (int j = 0; j < L; j++) {
+        const uint2 pm = prm.pm[j];
+        const cplx f = prm.f[j];
+        const double den = prm.dr[j].x;
+        const cplx sv = v2_stage[j * T + ((pm.x + pm.y * u) & (unsigned)(T - 1))];
+        const double ac = __dmul_rn(sv.x, f.x), bd = __dmul_rn(sv.y, f.y);
+        const double ad = __dmul_rn(sv.x, f.y), bc = __dmul_rn(sv.y, f.x);
+        const double qr = __ddiv_rn(__dadd_rn(ac, bd), den), qi = __ddiv_rn(__dsub_rn(ad, bc), den);
+        // the register arrays cannot be indexed dynamically: a predicated sweep puts the
+        // quotient in place (this path runs for exact zeros only)
+#pragma unroll
+        for (int t = 0; t < L; t++)
+          if (t == j) { vr[t] = qr; vi[t] = qi; }
+      }
+    }
+    __syncthreads();                               // every read of this tile's inputs is done
+    if (is_param && tile + 1 < t_end) issue_tile(tile + 1);
+
     const double re = MedianNet<L>::run(vr);
     const double im = MedianNet<L>::run(vi);
-    const long long o = idx - lo;
-    a.out_loc[o] = (int)((jj << a.logW) + (unsigned)__ldg(&a.approved[i]));      // cf12.cc:508-511
+    const unsigned c = (unsigned)(tile & ((1ll << sbits) - 1));
+    const unsigned jj = c + (u << sbits);
+    const long long o = (long long)sig * a.out_cap + ((tile - lo) << logT) + u;
+    a.out_loc[o] = (int)((jj << a.logW) + r);                                      // cf12.cc:508-511
     a.out_val[o] = make_double2(re, im);
   }
 }
@@ -756,39 +875,49 @@ bool v2_struct_supported(const LoopGeom &g, int logW)
     if (logW < logseg) return false;                 // W must be a multiple of the bucket width
   }
   const int logNW = g.logn - logW;
-  return logNW >= 5 && logNW <= 13 && g.loops >= 2 && g.loops <= 32;   // sub-row <= 128 KB
+  return logNW >= kV2LogTile && g.loops >= 2 && g.loops <= 32;
 }
 
-int launch_v2_struct(const LoopGeom &g, const V2StructArgs &a, int max_comb, cudaStream_t st)
+int v2_struct_log_tile(const LoopGeom &g, int logW)
+{
+  const int logNW = g.logn - logW;
+  return logNW < kV2LogTile ? logNW : kV2LogTile;
+}
+
+int launch_v2_struct(const LoopGeom &g, const V2StructArgs &a, int max_comb, int nsig, cudaStream_t st)
 {
   const int logNW = g.logn - a.logW;
-  int logq_max = 0;
-  for (int grp = 0; grp < 2; grp++) {
-    const int lq = a.logW - (g.logn - g.logB[grp]);
-    if (lq > logq_max) logq_max = lq;
-  }
-  const size_t smem = sizeof(cplx) << logNW;
-  static bool attr_set = false;
-  if (!attr_set) {
-    SFFTB_CUDA(cudaFuncSetAttribute(v2_values_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)(sizeof(cplx) << 13)));
-    attr_set = true;
-  }
-  dim3 grid(kV2Chunks, 1u << logq_max, (unsigned)g.loops);
-  v2_values_kernel<<<grid, kV2Threads, smem, st>>>(g, a);
+  const int logT = a.logT, T = 1 << logT;
+  const int maxlog = g.logB[0] > g.logB[1] ? g.logB[0] : g.logB[1];
+  dim3 rgrid((unsigned)ceil_div(1ll << maxlog, 256), (unsigned)g.loops, (unsigned)nsig);
+  v2_regroup_kernel<<<rgrid, 256, 0, st>>>(g, a.xs, a.xt, logT);
   SFFTB_LAUNCH_CHECK();
-  long long blocks = (((long long)max_comb << logNW) + 255) / 256;
-  if (blocks > 148ll * 16) blocks = 148ll * 16;
+  const size_t smem = sizeof(cplx) * (size_t)g.loops * T;
+  // persistent CTAs, as many as are resident at once (512 threads per SM)
+  long long ctas = 148ll * (512 >> kV2LogTile) / nsig;
+  const long long tiles = (long long)max_comb << (logNW - logT);
+  if (ctas < 1) ctas = 1;
+  if (ctas > tiles) ctas = tiles;
+  dim3 grid((unsigned)ctas, (unsigned)nsig);
   switch (g.loops) {
-#define SFFTB_V2M_CASE(N) case N: v2_median_kernel<N><<<(unsigned)blocks, 256, 0, st>>>(g, a); break;
-    SFFTB_V2M_CASE(2) SFFTB_V2M_CASE(3) SFFTB_V2M_CASE(4) SFFTB_V2M_CASE(5) SFFTB_V2M_CASE(6)
-    SFFTB_V2M_CASE(7) SFFTB_V2M_CASE(8) SFFTB_V2M_CASE(9) SFFTB_V2M_CASE(10) SFFTB_V2M_CASE(11)
-    SFFTB_V2M_CASE(12) SFFTB_V2M_CASE(13) SFFTB_V2M_CASE(14) SFFTB_V2M_CASE(15) SFFTB_V2M_CASE(16)
-    SFFTB_V2M_CASE(17) SFFTB_V2M_CASE(18) SFFTB_V2M_CASE(19) SFFTB_V2M_CASE(20) SFFTB_V2M_CASE(21)
-    SFFTB_V2M_CASE(22) SFFTB_V2M_CASE(23) SFFTB_V2M_CASE(24) SFFTB_V2M_CASE(25) SFFTB_V2M_CASE(26)
-    SFFTB_V2M_CASE(27) SFFTB_V2M_CASE(28) SFFTB_V2M_CASE(29) SFFTB_V2M_CASE(30) SFFTB_V2M_CASE(31)
-    SFFTB_V2M_CASE(32)
-#undef SFFTB_V2M_CASE
+#define SFFTB_V2F_CASE(N)                                                                         \
+  case N: {                                                                                       \
+    static bool attr_set = false;                                                                 \
+    if (!attr_set) {                                                                              \
+      SFFTB_CUDA(cudaFuncSetAttribute(v2_fused_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
+                                      (int)(sizeof(cplx) * N << kV2LogTile)));                    \
+      attr_set = true;                                                                            \
+    }                                                                                             \
+    v2_fused_kernel<N><<<grid, T, smem, st>>>(g, a);                                              \
+  } break;
+    SFFTB_V2F_CASE(2) SFFTB_V2F_CASE(3) SFFTB_V2F_CASE(4) SFFTB_V2F_CASE(5) SFFTB_V2F_CASE(6)
+    SFFTB_V2F_CASE(7) SFFTB_V2F_CASE(8) SFFTB_V2F_CASE(9) SFFTB_V2F_CASE(10) SFFTB_V2F_CASE(11)
+    SFFTB_V2F_CASE(12) SFFTB_V2F_CASE(13) SFFTB_V2F_CASE(14) SFFTB_V2F_CASE(15) SFFTB_V2F_CASE(16)
+    SFFTB_V2F_CASE(17) SFFTB_V2F_CASE(18) SFFTB_V2F_CASE(19) SFFTB_V2F_CASE(20) SFFTB_V2F_CASE(21)
+    SFFTB_V2F_CASE(22) SFFTB_V2F_CASE(23) SFFTB_V2F_CASE(24) SFFTB_V2F_CASE(25) SFFTB_V2F_CASE(26)
+    SFFTB_V2F_CASE(27) SFFTB_V2F_CASE(28) SFFTB_V2F_CASE(29) SFFTB_V2F_CASE(30) SFFTB_V2F_CASE(31)
+    SFFTB_V2F_CASE(32)
+#undef SFFTB_V2F_CASE
     default: set_error("launch_v2_struct: unsupported loop count"); return -1;
   }
   SFFTB_LAUNCH_CHECK();

@@ -79,22 +79,25 @@ int launch_estimate(const LoopGeom &g, const EstimateArgs &a, int nsig, long lon
 // v2's result list is {jj*W + r : r approved, jj < n/W} (cf12.cc:505-512).  For a fixed
 // loop j and residue r, ai_j*(jj*W + r) walks the buckets of ONE residue class modulo
 // q = W/(n/B) with a constant offset inside the bucket, visiting each of the n/W buckets
-// of that class exactly once.  So instead of 16.4 M x 20 random 16-byte L2 reads
-// (request-rate bound), phase 1 stages one class sub-row (n/W buckets) in shared memory
-// and streams the quotients out coalesced, V[j][i][jj]; phase 2 reads them back
-// coalesced and takes the medians.  Same arithmetic, same results.
+// of that class exactly once; restricted to jj == c (mod 2^s) it walks the n/W/2^s buckets
+// of one class modulo q*2^s.  So instead of 16.4 M x 20 random 16-byte L2 reads
+// (request-rate bound) a CTA owns one (r, c) tile of hits, copies the L bucket groups it
+// needs -- contiguous in a class-major copy `xt` of the spectra -- into shared memory, and
+// finishes divisions and medians in registers.  Same arithmetic, same results.
 struct V2StructArgs {
-  const int *perm;                 // a[loops], ai[loops]
-  const cplx *xs;                  // bucket spectra of this signal
+  const int *perm;                 // per signal: a[loops], ai[loops]
+  const cplx *xs;                  // bucket spectra            [nsig][x_samp_size]
+  cplx *xt;                        // class-major copy of them   [nsig][x_samp_size]
   const cplx *fwin[2]; int fw_half[2]; const double2 *fdr[2];
-  const int *approved; const int *num_comb;
+  const int *approved; long long approved_stride; const int *num_comb;
   int logW;                        // W_Comb = 2^logW
-  cplx *V;                         // [loops][num_comb][n/W]
+  int logT;                        // hits per tile = 2^logT (v2_struct_log_tile)
   int *out_loc; cplx *out_val; long long out_cap;
-  int slice_rank, slice_world; int *slice_count;
+  int slice_rank, slice_world; int *slice_count;   // slices are whole tiles
 };
 bool v2_struct_supported(const LoopGeom &g, int logW);
-int launch_v2_struct(const LoopGeom &g, const V2StructArgs &a, int max_comb, cudaStream_t st);
+int v2_struct_log_tile(const LoopGeom &g, int logW);
+int launch_v2_struct(const LoopGeom &g, const V2StructArgs &a, int max_comb, int nsig, cudaStream_t st);
 
 int launch_filter_den(const cplx *fwin, int len, double2 *fdr, cudaStream_t st);
 long long run_div_check(unsigned long long seed, long long count);
