@@ -60,6 +60,8 @@ struct PlanV12 {
   int *d_approved = nullptr;       // [cap][W]
   int *d_num_comb = nullptr;       // [cap]
   cplx *d_xt = nullptr;            // v2 structured estimation: class-major copy of d_xs
+  unsigned char *d_run_unsafe = nullptr;   // [cap][x_samp_size / tile]
+  unsigned *d_tile_counter = nullptr;      // [cap]
   int max_comb = 0;
   // per-transform draws: a[loops], ai[loops] per signal, then comb offsets
   int *d_stage = nullptr;          // [cap * ints_per_sig]

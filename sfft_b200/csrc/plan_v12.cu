@@ -202,6 +202,8 @@ static void v12_free_scratch(PlanV12 &v)
   cudaFree(v.d_count); cudaFree(v.d_comb_xs); cudaFree(v.d_comb_J); cudaFree(v.d_comb_bm);
   cudaFree(v.d_appr_bm); cudaFree(v.d_approved); cudaFree(v.d_num_comb); cudaFree(v.d_stage);
   cudaFree(v.d_xt); v.d_xt = nullptr;
+  cudaFree(v.d_run_unsafe); v.d_run_unsafe = nullptr;
+  cudaFree(v.d_tile_counter); v.d_tile_counter = nullptr;
   for (int i = 0; i < kStageSlots; i++) {
     if (v.h_stage[i]) cudaFreeHost(v.h_stage[i]);
     v.h_stage[i] = nullptr;
@@ -245,8 +247,11 @@ int v12_ensure_capacity(PlanImpl *p, int nsig)
     SFFTB_CUDA(cudaMalloc(&v.d_num_comb, sizeof(int) * S));
     if (W > 16384 && (long long)v.Comb_loops * W > gk) gk = (long long)v.Comb_loops * W;
     v.max_comb = (int)((long long)v.Comb_loops * num < W ? (long long)v.Comb_loops * num : W);
-    if (v2_struct_supported(v.geom, ilog2((unsigned)W)) && !getenv("SFFTB_NO_V2_STRUCT"))
+    if (v2_struct_supported(v.geom, ilog2((unsigned)W)) && !getenv("SFFTB_NO_V2_STRUCT")) {
       SFFTB_CUDA(cudaMalloc(&v.d_xt, sizeof(cplx) * S * v.x_samp_size));
+      SFFTB_CUDA(cudaMalloc(&v.d_run_unsafe, (size_t)(S * v.x_samp_size) >> v2_struct_log_tile(v.geom, ilog2((unsigned)W))));
+      SFFTB_CUDA(cudaMalloc(&v.d_tile_counter, sizeof(unsigned) * S));
+    }
   }
   v.gkeys_per_sig = gk;
   if (gk) SFFTB_CUDA(cudaMalloc(&v.d_gkeys, sizeof(unsigned long long) * S * gk));
@@ -439,6 +444,7 @@ static int v12_stage_finish(PlanImpl *p, int nsig, int slice_rank, int slice_wor
   if (v.with_comb && v.d_xt) {
     V2StructArgs sa2;
     sa2.perm = d_perm; sa2.xs = v.d_xs; sa2.xt = v.d_xt;
+    sa2.run_unsafe = v.d_run_unsafe; sa2.tile_counter = v.d_tile_counter;
     sa2.fwin[0] = ea.fwin[0]; sa2.fwin[1] = ea.fwin[1];
     sa2.fw_half[0] = ea.fw_half[0]; sa2.fw_half[1] = ea.fw_half[1];
     sa2.fdr[0] = ea.fdr[0]; sa2.fdr[1] = ea.fdr[1];

@@ -652,7 +652,8 @@ int launch_estimate(const LoopGeom &g, const EstimateArgs &a, int nsig, long lon
 // ---------------------------------------------------------------------------
 // v2 structured estimation (see v12_kernels.cuh)
 // ---------------------------------------------------------------------------
-constexpr int kV2LogTile = 8;         // hits per tile = threads per CTA (at most)
+constexpr int kV2LogTile = 8;         // hits per tile = threads per CTA
+constexpr int kV2MaxFlagBytes = 16384; // run flags kept in shared memory: x_samp_size <= 2^22
 
 __device__ __forceinline__ void v2_slice(const V2StructArgs &a, long long total, long long &lo, long long &hi)
 {
@@ -664,19 +665,31 @@ __device__ __forceinline__ void v2_slice(const V2StructArgs &a, long long total,
 }
 
 // class-major copy of every bucket spectrum: xt[(b mod 2^t) * T + (b >> t)] = xs[b],
-// T = 2^logT, t = logB - logT.  Buckets that agree modulo 2^t become contiguous.
-__global__ void v2_regroup_kernel(LoopGeom g, const cplx *__restrict__ xs, cplx *__restrict__ xt,
-                                  int logT)
+// T = 2^kV2LogTile, t = logB - kV2LogTile.  Buckets that agree modulo 2^t become one
+// contiguous run of T elements.  One CTA writes one run and records whether every
+// component of it lies in the exponent band where the fast division of the estimation
+// kernel is exact (nonzero, 2^-160 <= |x| < 2^190); it also resets the tile counter.
+__global__ void __launch_bounds__(1 << kV2LogTile)
+v2_regroup_kernel(LoopGeom g, const cplx *__restrict__ xs, cplx *__restrict__ xt,
+                  unsigned char *__restrict__ run_unsafe, unsigned *__restrict__ tile_counter)
 {
+  constexpr int logT = kV2LogTile;
   const int j = blockIdx.y;
   const long long sig = (long long)blockIdx.z * g.x_samp_size;
   const int logB = j >= g.loops_loc ? g.logB[1] : g.logB[0];
   const int t = logB - logT;
+  if (blockIdx.x == 0 && j == 0 && threadIdx.x == 0) tile_counter[blockIdx.z] = 0u;
   const unsigned o = blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= (1u << logB)) return;
   const unsigned b = (o >> logT) | ((o & ((1u << logT) - 1u)) << t);
   const long long off = sig + loop_offset(g, j);
-  xt[off + o] = xs[off + b];
+  const cplx v = xs[off + b];
+  xt[off + o] = v;
+  const unsigned ex = ((unsigned)__double2hiint(v.x) >> 20) & 0x7ffu;
+  const unsigned ey = ((unsigned)__double2hiint(v.y) >> 20) & 0x7ffu;
+  const int bad = (ex - (1023u - 160u) >= 350u) || (ey - (1023u - 160u) >= 350u);
+  const int any = __syncthreads_or(bad);
+  if (threadIdx.x == 0) run_unsafe[(off + o) >> logT] = (unsigned char)any;
 }
 
 // per-(tile, loop) constants, split so that every access is one aligned vector load
@@ -685,12 +698,17 @@ struct V2TileParams {
   double2 dr[32];      // (|f|^2, RN(1/|f|^2))
   uint2 pm[32];        // element of hit u: (pm.x + pm.y*u) mod T
   unsigned r;          // the tile's residue
-  int den_unsafe;      // some |f|^2 outside div_fast's exponent band (sticky)
+  int unsafe;          // this tile must use real divisions
+  unsigned chunk;      // first chunk claimed by the CTA
+  long long tile;      // the tile these parameters belong to; -1: no more tiles
 };
 
-// a / b with y = RN(1/b): as div_by_rcp_rn without the guard; the caller checks the
-// exponents of every numerator once per hit and redoes the hit with real divisions
-// when one falls outside the band (exact zeros, in practice).
+// a / b with y = RN(1/b): two Markstein corrections, as div_by_rcp_rn without the guard.
+// Exact (== __ddiv_rn) when 2^-383 <= |a|,|b| < 2^385 or a == +0.  The estimation kernel
+// guarantees that per tile instead of per division: numerators are sums of two products
+// of a spectrum component and a filter component; with every spectrum component of the
+// tile's runs in [2^-160, 2^190) (v2_regroup_kernel) and every filter component zero or in
+// that band (not both zero), a numerator is +0 (exact cancellation) or in [2^-373, 2^381).
 __device__ __forceinline__ double div_fast(double a, double b, double y)
 {
   double q = __dmul_rn(a, y);
@@ -729,23 +747,39 @@ __device__ __forceinline__ void bulk_copy_g2s(unsigned dst, const void *src, uns
                ::"r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
 }
 
+__device__ __forceinline__ bool v2_band_or_zero(double x)
+{
+  const unsigned h = (unsigned)__double2hiint(x) & 0x7fffffffu;
+  return (h | (unsigned)__double2loint(x)) == 0u || ((h >> 20) - (1023u - 160u)) < 350u;
+}
+
+constexpr int kV2Chunk = 4;           // tiles claimed per atomic
+
+__device__ __forceinline__ void mbar_arrive(unsigned bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+
 // Tile = (residue i, jj mod 2^s == c): T = (n/W)/2^s hits, one per thread.  In loop j those
 // hits read T buckets that agree modulo q*2^s -- one contiguous 16*T-byte run of xt -- so
 // L bulk copies bring the tile's inputs into shared memory; each thread picks its L values,
 // divides by the filter response, keeps the 2L quotients in registers and takes the two
-// medians.  No intermediate leaves the SM.  CTAs are persistent over a contiguous range of
-// tiles: while the medians of tile t run, the copies for tile t+1 are already in flight
-// (issued by the L parameter threads right after the last read of tile t's inputs), and
-// the per-residue constants are only reloaded when the residue changes.
+// medians.  No intermediate leaves the SM.
+// CTAs are persistent and claim chunks of consecutive tiles from a counter.  Two mbarriers
+// pipeline them: `full` (the L copies of a tile have landed, parameters are written) and
+// `empty` (every warp has read its inputs).  The L parameter threads wait on `empty`, write
+// the next tile's parameters and issue its copies; everybody else goes straight from the
+// divisions to the medians, so the copies fly under the medians and warps of one CTA
+// drift apart by up to a phase -- FP64-heavy divisions and ALU-heavy medians overlap.
 template <int L>
 __global__ void __launch_bounds__(1 << kV2LogTile, 512 >> kV2LogTile)
 v2_fused_kernel(LoopGeom g, V2StructArgs a)
 {
   constexpr int logT = kV2LogTile, T = 1 << logT;
   constexpr unsigned kRunBytes = T * sizeof(cplx);
-  extern __shared__ __align__(128) cplx v2_stage[];              // [L][T]
+  extern __shared__ __align__(128) cplx v2_stage[];              // [L][T], then the run flags
   __shared__ V2TileParams prm;
-  __shared__ __align__(8) unsigned long long full_bar;
+  __shared__ __align__(8) unsigned long long bars[2];            // full, empty
   const int sig = blockIdx.y;
   const int logNW = g.logn - a.logW;
   const int sbits = logNW - logT;
@@ -753,23 +787,30 @@ v2_fused_kernel(LoopGeom g, V2StructArgs a)
   long long lo, hi;
   v2_slice(a, (long long)nc << sbits, lo, hi);
   if (a.slice_count && blockIdx.x == 0 && threadIdx.x == 0) a.slice_count[0] = (int)((hi - lo) << logT);
-  const long long t_begin = lo + (hi - lo) * blockIdx.x / gridDim.x;
-  const long long t_end = lo + (hi - lo) * (blockIdx.x + 1) / gridDim.x;
-  if (t_begin >= t_end) return;
   const unsigned u = threadIdx.x;
   const unsigned stage0 = (unsigned)__cvta_generic_to_shared(v2_stage);
-  const unsigned bar = (unsigned)__cvta_generic_to_shared(&full_bar);
+  const unsigned full = (unsigned)__cvta_generic_to_shared(&bars[0]);
+  const unsigned empty = (unsigned)__cvta_generic_to_shared(&bars[1]);
   const cplx *__restrict__ xt = a.xt + (long long)sig * g.x_samp_size;
+  unsigned char *s_unsafe = reinterpret_cast<unsigned char *>(v2_stage + L * T);
+  unsigned *ctr = a.tile_counter + sig;
 
+  {
+    const int nruns = (int)(g.x_samp_size >> logT);
+    const unsigned char *src = a.run_unsafe + (((long long)sig * g.x_samp_size) >> logT);
+    for (int t = (int)u; t < nruns; t += T) s_unsafe[t] = src[t];
+  }
   if (u == 0) {
-    mbar_init(bar, L);
-    prm.den_unsafe = 0;
+    mbar_init(full, L);
+    mbar_init(empty, T / 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    prm.chunk = atomicAdd(ctr, 1u);
   }
   __syncthreads();
 
   // ---- parameter threads: loop j = u ----
   const bool is_param = u < (unsigned)L;
+  const unsigned param_mask = L == 32 ? 0xffffffffu : ((1u << L) - 1u);
   const int pj = is_param ? (int)u : 0;
   const bool p_est = pj >= g.loops_loc;
   const int p_logB = p_est ? g.logB[1] : g.logB[0];
@@ -780,7 +821,19 @@ v2_fused_kernel(LoopGeom g, V2StructArgs a)
   const unsigned p_off = (unsigned)loop_offset(g, pj);
   int p_i = -1;
   unsigned p_bucket = 0;
-  auto issue_tile = [&](long long tile) {
+  bool p_fbad = false;
+  long long p_tile = lo + (long long)prm.chunk * kV2Chunk;      // next tile to issue
+  long long p_chunk_end = p_tile + kV2Chunk;
+  unsigned p_pending = 0;
+  // writes the parameters of tile `p_tile` (or the end marker) and releases `full`
+  auto issue_tile = [&]() {
+    if (p_tile >= hi) {
+      if (pj == 0) prm.tile = -1;
+      mbar_arrive(full);
+      return;
+    }
+    const long long tile = p_tile;
+    if (pj == 0 && tile + kV2Chunk == p_chunk_end) p_pending = atomicAdd(ctr, 1u);   // first of its chunk
     const int i = (int)(tile >> sbits);
     const unsigned c = (unsigned)(tile & ((1ll << sbits) - 1));
     if (i != p_i) {
@@ -797,30 +850,41 @@ v2_fused_kernel(LoopGeom g, V2StructArgs a)
       p_bucket = bucket;
       const int half = p_est ? a.fw_half[1] : a.fw_half[0];
       const double2 dr = __ldg(&(p_est ? a.fdr[1] : a.fdr[0])[half - dist]);
-      prm.f[pj] = __ldg(&(p_est ? a.fwin[1] : a.fwin[0])[half - dist]);
+      const cplx f = __ldg(&(p_est ? a.fwin[1] : a.fwin[0])[half - dist]);
+      prm.f[pj] = f;
       prm.dr[pj] = dr;
       if (pj == 0) prm.r = r;
       const unsigned eb = ((unsigned)__double2hiint(dr.x) >> 20) & 0x7ffu;
-      if (eb - 640u >= 768u) prm.den_unsafe = 1;
+      p_fbad = (eb - 640u >= 768u) || !v2_band_or_zero(f.x) || !v2_band_or_zero(f.y);
     }
     const unsigned cls = p_bucket & ((1u << p_logq) - 1u);
     const unsigned P = ((p_bucket >> p_logq) + p_m * c) & (unsigned)((1 << logNW) - 1);
     const unsigned beta = cls | ((P & ((1u << sbits) - 1u)) << p_logq);
+    const unsigned run0 = p_off + (beta << logT);
     prm.pm[pj] = make_uint2((P >> sbits) & (unsigned)(T - 1), p_m & (unsigned)(T - 1));
+    const int bad = __any_sync(param_mask, p_fbad || s_unsafe[run0 >> logT]);
+    if (pj == 0) { prm.unsafe = bad; prm.tile = tile; }
     // the CTA's reads of the previous tile (generic proxy) precede this copy (async proxy)
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-    mbar_arrive_expect_tx(bar, kRunBytes);
-    bulk_copy_g2s(stage0 + (unsigned)pj * kRunBytes, xt + p_off + (beta << logT), kRunBytes, bar);
+    mbar_arrive_expect_tx(full, kRunBytes);
+    bulk_copy_g2s(stage0 + (unsigned)pj * kRunBytes, xt + run0, kRunBytes, full);
+    // advance: within the chunk, or to the chunk claimed while this one was running
+    p_tile = tile + 1;
+    if (p_tile == p_chunk_end) {
+      p_tile = lo + (long long)__shfl_sync(param_mask, p_pending, 0) * kV2Chunk;
+      p_chunk_end = p_tile + kV2Chunk;
+    }
   };
-  if (is_param) issue_tile(t_begin);
+  if (is_param) issue_tile();
 
   unsigned parity = 0;
-  for (long long tile = t_begin; tile < t_end; tile++) {
-    mbar_wait(bar, parity);
-    parity ^= 1u;
+  while (true) {
+    mbar_wait(full, parity);
+    const long long tile = prm.tile;
+    if (tile < 0) break;
     const unsigned r = prm.r;
+    const int unsafe = prm.unsafe;
     double vr[L], vi[L];
-    unsigned emin = 0x7fffffffu, emax = 0u;
 #pragma unroll
     for (int j = 0; j < L; j++) {
       const uint2 pm = prm.pm[j];
@@ -829,16 +893,11 @@ v2_fused_kernel(LoopGeom g, V2StructArgs a)
       const cplx sv = lds_cplx(stage0 + (unsigned)j * kRunBytes + (((pm.x + pm.y * u) & (unsigned)(T - 1)) << 4));
       const double ac = __dmul_rn(sv.x, f.x), bd = __dmul_rn(sv.y, f.y);
       const double ad = __dmul_rn(sv.x, f.y), bc = __dmul_rn(sv.y, f.x);
-      const double nr = __dadd_rn(ac, bd), ni = __dsub_rn(ad, bc);                  // :388-398
-      const unsigned hr = (unsigned)__double2hiint(nr) & 0x7fffffffu;
-      const unsigned hi2 = (unsigned)__double2hiint(ni) & 0x7fffffffu;
-      emin = min(emin, min(hr, hi2));
-      emax = max(emax, max(hr, hi2));
-      vr[j] = div_fast(nr, dr.x, dr.y);
-      vi[j] = div_fast(ni, dr.x, dr.y);
+      vr[j] = div_fast(__dadd_rn(ac, bd), dr.x, dr.y);                             // :388-398
+      vi[j] = div_fast(__dsub_rn(ad, bc), dr.x, dr.y);
     }
-    if (emin < (640u << 20) || emax >= (1408u << 20) || prm.den_unsafe) {
-      // a numerator (or denominator) outside the band where div_fast is proven: redo exactly
+    if (unsafe) {
+      // some input of this tile is zero or outside the band where div_fast is proven
 #pragma unroll 1
       for (int j = 0; j < L; j++) {
         const uint2 pm = prm.pm[j];
@@ -849,14 +908,20 @@ v2_fused_kernel(LoopGeom g, V2StructArgs a)
         const double ad = __dmul_rn(sv.x, f.y), bc = __dmul_rn(sv.y, f.x);
         const double qr = __ddiv_rn(__dadd_rn(ac, bd), den), qi = __ddiv_rn(__dsub_rn(ad, bc), den);
         // the register arrays cannot be indexed dynamically: a predicated sweep puts the
-        // quotient in place (this path runs for exact zeros only)
+        // quotient in place
 #pragma unroll
         for (int t = 0; t < L; t++)
           if (t == j) { vr[t] = qr; vi[t] = qi; }
       }
     }
-    __syncthreads();                               // every read of this tile's inputs is done
-    if (is_param && tile + 1 < t_end) issue_tile(tile + 1);
+    // this warp is done with the tile's inputs and parameters
+    __syncwarp();
+    if ((u & 31u) == 0) mbar_arrive(empty);
+    if (is_param) {
+      mbar_wait(empty, parity);
+      issue_tile();
+    }
+    parity ^= 1u;
 
     const double re = MedianNet<L>::run(vr);
     const double im = MedianNet<L>::run(vi);
@@ -875,7 +940,8 @@ bool v2_struct_supported(const LoopGeom &g, int logW)
     if (logW < logseg) return false;                 // W must be a multiple of the bucket width
   }
   const int logNW = g.logn - logW;
-  return logNW >= kV2LogTile && g.loops >= 2 && g.loops <= 32;
+  return logNW >= kV2LogTile && g.loops >= 2 && g.loops <= 32 &&
+         (g.x_samp_size >> kV2LogTile) <= kV2MaxFlagBytes && g.logB[0] >= kV2LogTile && g.logB[1] >= kV2LogTile;
 }
 
 int v2_struct_log_tile(const LoopGeom &g, int logW)
@@ -887,17 +953,18 @@ int v2_struct_log_tile(const LoopGeom &g, int logW)
 int launch_v2_struct(const LoopGeom &g, const V2StructArgs &a, int max_comb, int nsig, cudaStream_t st)
 {
   const int logNW = g.logn - a.logW;
-  const int logT = a.logT, T = 1 << logT;
+  constexpr int logT = kV2LogTile, T = 1 << logT;
   const int maxlog = g.logB[0] > g.logB[1] ? g.logB[0] : g.logB[1];
-  dim3 rgrid((unsigned)ceil_div(1ll << maxlog, 256), (unsigned)g.loops, (unsigned)nsig);
-  v2_regroup_kernel<<<rgrid, 256, 0, st>>>(g, a.xs, a.xt, logT);
+  dim3 rgrid(1u << (maxlog - logT), (unsigned)g.loops, (unsigned)nsig);
+  v2_regroup_kernel<<<rgrid, T, 0, st>>>(g, a.xs, a.xt, a.run_unsafe, a.tile_counter);
   SFFTB_LAUNCH_CHECK();
-  const size_t smem = sizeof(cplx) * (size_t)g.loops * T;
+  const size_t flag_bytes = ((size_t)(g.x_samp_size >> logT) + 15) & ~(size_t)15;
+  const size_t smem = sizeof(cplx) * (size_t)g.loops * T + flag_bytes;
   // persistent CTAs, as many as are resident at once (512 threads per SM)
   long long ctas = 148ll * (512 >> kV2LogTile) / nsig;
-  const long long tiles = (long long)max_comb << (logNW - logT);
+  const long long chunks = (((long long)max_comb << (logNW - logT)) + kV2Chunk - 1) / kV2Chunk;
   if (ctas < 1) ctas = 1;
-  if (ctas > tiles) ctas = tiles;
+  if (ctas > chunks) ctas = chunks;
   dim3 grid((unsigned)ctas, (unsigned)nsig);
   switch (g.loops) {
 #define SFFTB_V2F_CASE(N)                                                                         \
@@ -905,7 +972,7 @@ int launch_v2_struct(const LoopGeom &g, const V2StructArgs &a, int max_comb, int
     static bool attr_set = false;                                                                 \
     if (!attr_set) {                                                                              \
       SFFTB_CUDA(cudaFuncSetAttribute(v2_fused_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                      (int)(sizeof(cplx) * N << kV2LogTile)));                    \
+                                      (int)(sizeof(cplx) * N << kV2LogTile) + kV2MaxFlagBytes));  \
       attr_set = true;                                                                            \
     }                                                                                             \
     v2_fused_kernel<N><<<grid, T, smem, st>>>(g, a);                                              \
