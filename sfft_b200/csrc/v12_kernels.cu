@@ -652,8 +652,8 @@ int launch_estimate(const LoopGeom &g, const EstimateArgs &a, int nsig, long lon
 // ---------------------------------------------------------------------------
 // v2 structured estimation (see v12_kernels.cuh)
 // ---------------------------------------------------------------------------
-constexpr int kV2LogTile = 8;         // hits per tile = threads per CTA
-constexpr int kV2MaxFlagBytes = 16384; // run flags kept in shared memory: x_samp_size <= 2^22
+constexpr int kV2LogTile = 9;         // hits per tile = threads per CTA (one CTA per SM; 8 KB runs)
+constexpr int kV2MaxSmem = 227 * 1024 - 8192;   // dynamic shared memory a CTA may ask for (static: parameters)
 
 __device__ __forceinline__ void v2_slice(const V2StructArgs &a, long long total, long long &lo, long long &hi)
 {
@@ -940,8 +940,10 @@ bool v2_struct_supported(const LoopGeom &g, int logW)
     if (logW < logseg) return false;                 // W must be a multiple of the bucket width
   }
   const int logNW = g.logn - logW;
+  const long long flag_bytes = ((g.x_samp_size >> kV2LogTile) + 15) & ~15ll;
   return logNW >= kV2LogTile && g.loops >= 2 && g.loops <= 32 &&
-         (g.x_samp_size >> kV2LogTile) <= kV2MaxFlagBytes && g.logB[0] >= kV2LogTile && g.logB[1] >= kV2LogTile;
+         ((long long)sizeof(cplx) * g.loops << kV2LogTile) + flag_bytes <= kV2MaxSmem &&
+         g.logB[0] >= kV2LogTile && g.logB[1] >= kV2LogTile;
 }
 
 int v2_struct_log_tile(const LoopGeom &g, int logW)
@@ -972,7 +974,7 @@ int launch_v2_struct(const LoopGeom &g, const V2StructArgs &a, int max_comb, int
     static bool attr_set = false;                                                                 \
     if (!attr_set) {                                                                              \
       SFFTB_CUDA(cudaFuncSetAttribute(v2_fused_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                      (int)(sizeof(cplx) * N << kV2LogTile) + kV2MaxFlagBytes));  \
+                                      kV2MaxSmem));                                               \
       attr_set = true;                                                                            \
     }                                                                                             \
     v2_fused_kernel<N><<<grid, T, smem, st>>>(g, a);                                              \

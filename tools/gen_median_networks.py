@@ -207,6 +207,7 @@ def main():
              "(a) = s_ ? y_ : x_; (b) = s_ ? x_ : y_; }\n",
              "#define SFFTB_MIN(a, b) ((b) < (a) ? (b) : (a))\n",
              "#define SFFTB_MAX(a, b) ((b) < (a) ? (a) : (b))\n",
+             "template <int K> struct IntC { static constexpr int value = K; };\n",
              "template <int L> struct MedianNet;\n"]
     for n in range(LMIN, LMAX + 1):
         a = construction_a(n)
@@ -228,6 +229,28 @@ def main():
                 if op[1] >= n and op[1] not in declared:
                     declared.add(op[1]); decl = "const double "
                 lines.append(f"    {decl}{d} = {macro}({name(op[2], n)}, {name(op[3], n)});\n")
+        lines.append(f"    return {name(want, n)};\n  }}\n")
+        # same network with L evenly spaced hooks: side(IntC<k>) runs between its operations, so
+        # independent work (FP64 divisions) can be interleaved with the ALU-bound selects
+        lines.append(f"  template <class F> static __device__ __forceinline__ double run_with(double (&v)[{n}], F &&side) {{\n")
+        declared = set()
+        hooks = 0
+        for t, op in enumerate(ops):
+            while hooks < n and hooks * len(ops) <= t * n:
+                lines.append(f"    side(IntC<{hooks}>());\n")
+                hooks += 1
+            if op[0] == "cs":
+                lines.append(f"    SFFTB_CSWAP({name(op[1], n)}, {name(op[2], n)})\n")
+            else:
+                d = name(op[1], n)
+                macro = "SFFTB_MIN" if op[0] == "min" else "SFFTB_MAX"
+                decl = ""
+                if op[1] >= n and op[1] not in declared:
+                    declared.add(op[1]); decl = "const double "
+                lines.append(f"    {decl}{d} = {macro}({name(op[2], n)}, {name(op[3], n)});\n")
+        while hooks < n:
+            lines.append(f"    side(IntC<{hooks}>());\n")
+            hooks += 1
         lines.append(f"    return {name(want, n)};\n  }}\n}};\n")
         print(n, tag, "compares", compares, "selects", selects, "| A", a[2], a[1], "| B", b[2], b[1])
     lines.append("#undef SFFTB_CSWAP\n#undef SFFTB_MIN\n#undef SFFTB_MAX\n")
