@@ -424,10 +424,14 @@ def run_ours(args):
                 return None
             b = batch * stage_bytes(info, stage, count)
             ach = b / (ms * 1e-3) / 1e9
-            return {"kernel": stage, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                    "frac": ach / hbm_peak, "traffic": traffic.get(stage), "ms": ms, "algorithmic_bytes": b,
-                    "peak_source": peak_src,
-                    "traffic_source": "ncu dram bytes per launch, profiles/r01_traffic.json" if stage in traffic else None}
+            r = {"kernel": stage, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
+                 "frac": ach / hbm_peak, "traffic": traffic.get(stage), "ms": ms, "algorithmic_bytes": b,
+                 "peak_source": peak_src,
+                 "traffic_source": "ncu dram bytes per launch, profiles/r01_traffic.json" if stage in traffic else None}
+            note = traffic.get(stage + "_note")
+            if note:
+                r["note"] = note
+            return r
 
         dominant = max(stages, key=stages.get) if stages else None
         line = {

@@ -14,11 +14,13 @@ KEYS = [
     ("gpu__time_duration.sum", "time"),
     ("dram__bytes_read.sum", "dram_rd"),
     ("dram__bytes_write.sum", "dram_wr"),
-    ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram%"),
+    ("dram__bytes_read.sum.pct_of_peak_sustained_elapsed", "dram_rd%"),
+    ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue%"),
+    ("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "alu%"),
     ("lts__throughput.avg.pct_of_peak_sustained_elapsed", "l2%"),
     ("l1tex__throughput.avg.pct_of_peak_sustained_active", "l1%"),
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm%"),
-    ("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "fp64%"),
+    ("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active", "fp64%"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "occ%"),
     ("lts__t_sector_hit_rate.pct", "l2hit%"),
     ("l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum", "ld_sectors"),
@@ -81,6 +83,18 @@ def launches(path):
     for nm, (c, us) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print(f"{nm:46s} {c:9d} {us:12.2f} {us / c:10.2f} {100 * us / total:8.2f}")
     print(f"{'TOTAL':46s} {sum(c for c, _ in agg.values()):9d} {total:12.2f}")
+    # the same list restricted to the kernels of a transform (the plan builder's FFTs and
+    # sequential chains, torch's input synthesis and the legacy dense scatter run outside the
+    # timed region): these shares are the ones to compare with bench.py's stage_ms
+    xform = {nm: v for nm, v in agg.items()
+             if re.match(r"(gather_kernel|select_kernel|vote_kernel|estimate_|v2_|comb_|fft_pass_kernel<[01]>|"
+                         r"(<unnamed>::)?v3_)", nm)}
+    xt = sum(us for _, us in xform.values())
+    if xt > 0:
+        print()
+        print(f"{'transform kernels only':46s} {'launches':>9s} {'total_us':>12s} {'avg_us':>10s} {'share%':>8s}")
+        for nm, (c, us) in sorted(xform.items(), key=lambda kv: -kv[1][1]):
+            print(f"{nm:46s} {c:9d} {us:12.2f} {us / c:10.2f} {100 * us / xt:8.2f}")
 
 
 if __name__ == "__main__":
