@@ -35,6 +35,8 @@ WORKLOADS = {
     # name: (version, n, k, noisy_snr_db or None, description)
     "C1": (1, 1 << 22, 50, None, "sFFT v1 exact k-sparse n=2^22 k=50"),
     "C2": (2, 1 << 24, 1000, None, "sFFT v2 (Comb) exact k-sparse n=2^24 k=1000"),
+    # the nearest v2 point the as-shipped (asserts on) reference can run
+    "C2b": (2, 1 << 24, 50, None, "sFFT v2 (Comb) exact k-sparse n=2^24 k=50"),
     "C3": (3, 1 << 26, 2000, None, "sFFT v3 exact-sparse n=2^26 k=2000"),
     "C4": (1, 1 << 27, 500, 20.0, "sFFT v1 noisy 20 dB n=2^27 k=500"),
     "C5": (1, 1 << 20, 100, None, "sFFT v1 n=2^20 k=100, sfft_exec_many batch of 256 signals per step"),

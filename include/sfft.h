@@ -55,6 +55,12 @@ typedef struct sfft_plan {
  * accepted and ignored here: there is no FFTW behind this library. */
 #define SFFT_FFTW_MEASURE 0
 #define SFFT_FFTW_ESTIMATE 64
+/* Opt-in bit for the fftw_optimization word of sfft_make_plan (FFTW's planner flags end at
+ * bit 21): look the tuned parameters of a k > 50 plan up BY k, as src/parameters.cc:282-513
+ * was written for (tuned at n = 2^22).  The reference passes n as the key
+ * (src/sfft.cc:316-321), so the lookup never matches and such plans run on the defaults;
+ * without this bit this library does exactly the same.  Parity claims hold without it. */
+#define SFFTB_PLAN_TUNED_BY_K (1 << 24)
 
 /* reference src/sfft.cc:60-69 (_mm_malloc(s,16)).  Here: page-locked host memory
  * (cudaHostAlloc) so the H2D/D2H legs of sfft_exec run at PCIe speed; falls back
@@ -186,6 +192,15 @@ int sfftb_shard_spectra(sfft_plan *plan, void **d_spectra, long long *n_doubles)
 int sfftb_shard_finish(sfft_plan *plan, int rank, int world, sfftb_result *result, int sync);
 /* loops [begin, end) of the plan's `loops` that `rank` owns (block partition) */
 int sfftb_shard_loops(const sfft_plan *plan, int rank, int world, int *begin, int *end);
+
+/* ---- plan cache ----------------------------------------------
+ * A plan is (n, k, version, flags) plus its two filters; everything else is derived.
+ * sfftb_save_plan writes them to a file; sfftb_load_plan re-creates the plan from it
+ * without running the filter builder (seconds at n >= 2^26; the reference needs minutes,
+ * src/filters.cc:70-160).  The loaded plan is bit-identical to the saved one.
+ * Returns 0 / a plan, or -1 / NULL with sfftb_last_error() set. */
+int sfftb_save_plan(const sfft_plan *plan, const char *path);
+sfft_plan *sfftb_load_plan(const char *path);
 
 /* ---- plan-builder hooks (parity injection / plan cache) ------------------ */
 /* which: 0 = location filter, 1 = estimation filter (v1/v2); 0/1 = first/second

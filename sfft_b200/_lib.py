@@ -70,6 +70,8 @@ SYMBOLS = {
                                      C.POINTER(_ll), _ci]),
     "sfftb_densify": (_ci, [_PP, _ci, _vp]),
     "sfftb_synchronize": (_ci, [_PP]),
+    "sfftb_save_plan": (_ci, [_PP, C.c_char_p]),
+    "sfftb_load_plan": (_PP, [C.c_char_p]),
     "sfftb_fetch_result": (_ll, [_PP, _ci, _vp, _vp, _ll]),
     "sfftb_shard_bucketize": (_ci, [_PP, _vp, C.POINTER(Draw), _ci, _ci]),
     "sfftb_shard_spectra": (_ci, [_PP, C.POINTER(_vp), C.POINTER(_ll)]),

@@ -105,7 +105,8 @@ void sfft_free(void *p)
 
 sfft_plan *sfft_make_plan(int n, int k, sfft_version version, int fftw_optimization)
 {
-  (void)fftw_optimization;   // accepted and ignored: no FFTW here (python/sfft/sfft.py:74 ignores it too)
+  // FFTW planner flags are accepted and ignored: no FFTW here (python/sfft/sfft.py:74 passes
+  // them through); SFFTB_PLAN_TUNED_BY_K is this library's own opt-in bit
   if (version != SFFT_VERSION_1 && version != SFFT_VERSION_2 && version != SFFT_VERSION_3) {
     set_error("sfft_make_plan: unknown version (reference returns NULL, sfft.cc:87-88)");
     return nullptr;
@@ -125,11 +126,12 @@ sfft_plan *sfft_make_plan(int n, int k, sfft_version version, int fftw_optimizat
   }
   p->stream = p->own_stream;
   p->version = (int)version + 1;
+  p->flags = fftw_optimization;
   int rc;
   if (version == SFFT_VERSION_3) {
     rc = v3_build(p, n, k);
   } else {
-    rc = v12_derive(p, n, k, version == SFFT_VERSION_2);
+    rc = v12_derive(p, n, k, version == SFFT_VERSION_2, (fftw_optimization & SFFTB_PLAN_TUNED_BY_K) != 0);
     if (!rc) rc = v12_build(p);
   }
   if (rc) {
@@ -427,6 +429,75 @@ int sfftb_set_filter(sfft_plan *plan, int which, const sfft_complex *time, const
   return 0;
 }
 
+/* ---- plan cache ---- */
+namespace {
+struct PlanFileHeader {
+  char magic[8];
+  int version, n, k, flags, nfilt;
+  int w[2], fw_half[2];
+};
+const char kPlanMagic[8] = {'S', 'F', 'F', 'T', 'B', 'P', 'L', '1'};
+}
+
+int sfftb_save_plan(const sfft_plan *plan, const char *path)
+{
+  PlanImpl *p = impl(plan);
+  if (!p || !path) { set_error("sfftb_save_plan: null argument"); return -1; }
+  PlanFileHeader h;
+  memset(&h, 0, sizeof h);
+  memcpy(h.magic, kPlanMagic, 8);
+  h.version = p->version - 1; h.n = p->n; h.k = p->k; h.flags = p->flags; h.nfilt = 2;
+  std::vector<std::vector<cplx>> time(2), fwin(2);
+  for (int f = 0; f < 2; f++) {
+    int w = 0, len = 0;
+    if (sfftb_filter_sizes(plan, f, &w, &len)) return -1;
+    h.w[f] = w; h.fw_half[f] = (len - 1) / 2;
+    time[f].resize((size_t)w); fwin[f].resize((size_t)len);
+    if (sfftb_get_filter(plan, f, (sfft_complex *)time[f].data(), (sfft_complex *)fwin[f].data())) return -1;
+  }
+  FILE *fp = fopen(path, "wb");
+  if (!fp) { set_error(std::string("sfftb_save_plan: cannot open ") + path); return -1; }
+  bool ok = fwrite(&h, sizeof h, 1, fp) == 1;
+  for (int f = 0; f < 2 && ok; f++) {
+    ok = fwrite(time[f].data(), sizeof(cplx), time[f].size(), fp) == time[f].size() &&
+         fwrite(fwin[f].data(), sizeof(cplx), fwin[f].size(), fp) == fwin[f].size();
+  }
+  ok = fclose(fp) == 0 && ok;
+  if (!ok) { set_error(std::string("sfftb_save_plan: short write to ") + path); return -1; }
+  return 0;
+}
+
+sfft_plan *sfftb_load_plan(const char *path)
+{
+  if (!path) { set_error("sfftb_load_plan: null path"); return nullptr; }
+  FILE *fp = fopen(path, "rb");
+  if (!fp) { set_error(std::string("sfftb_load_plan: cannot open ") + path); return nullptr; }
+  PlanFileHeader h;
+  bool ok = fread(&h, sizeof h, 1, fp) == 1 && memcmp(h.magic, kPlanMagic, 8) == 0 && h.nfilt == 2 &&
+            h.version >= 0 && h.version <= 2;
+  std::vector<std::vector<cplx>> time(2), fwin(2);
+  for (int f = 0; f < 2 && ok; f++) {
+    ok = h.w[f] > 0 && h.fw_half[f] >= 0 && h.w[f] <= h.n && h.fw_half[f] < h.n;
+    if (!ok) break;
+    time[f].resize((size_t)h.w[f]);
+    fwin[f].resize((size_t)(2ll * h.fw_half[f] + 1));
+    ok = fread(time[f].data(), sizeof(cplx), time[f].size(), fp) == time[f].size() &&
+         fread(fwin[f].data(), sizeof(cplx), fwin[f].size(), fp) == fwin[f].size();
+  }
+  fclose(fp);
+  if (!ok) { set_error(std::string("sfftb_load_plan: not a plan file, or truncated: ") + path); return nullptr; }
+  PresetFilters pre;
+  pre.count = 2;
+  for (int f = 0; f < 2; f++) {
+    pre.w[f] = h.w[f]; pre.fw_half[f] = h.fw_half[f];
+    pre.time[f] = time[f].data(); pre.fwin[f] = fwin[f].data();
+  }
+  set_preset_filters(&pre);
+  sfft_plan *plan = sfft_make_plan(h.n, h.k, (sfft_version)h.version, h.flags);
+  set_preset_filters(nullptr);     // in case plan creation failed before reaching the builder
+  return plan;
+}
+
 /* ---- stage hooks ---- */
 long long sfftb_debug_fetch(sfft_plan *plan, const char *what, void *dst, size_t capacity)
 {
@@ -514,12 +585,12 @@ int sfftb_debug_select(const double *mags, int B, int num, int batch, int *out_J
   SFFTB_CUDA(cudaMalloc(&d_x, sizeof(cplx) * total));
   SFFTB_CUDA(cudaMalloc(&d_J, sizeof(int) * (long long)num * batch));
   SFFTB_CUDA(cudaMalloc(&d_bm, sizeof(unsigned) * (long long)words * batch));
-  if (B > 16384) SFFTB_CUDA(cudaMalloc(&d_k, sizeof(unsigned long long) * total));
+  if (B > 16384) SFFTB_CUDA(cudaMalloc(&d_k, sizeof(unsigned long long) * select_gkeys_per_row(B) * batch));
   SFFTB_CUDA(cudaMemcpy(d_x, h.data(), sizeof(cplx) * total, cudaMemcpyHostToDevice));
   SelectArgs sa;
   sa.xs = d_x; sa.xs_stride = 0; sa.row_stride = B; sa.logB = ilog2((unsigned)B); sa.num = num;
   sa.J = d_J; sa.J_sig_stride = 0; sa.bitmap = d_bm; sa.bm_sig_stride = 0;
-  sa.gkeys = d_k; sa.gk_sig_stride = 0; sa.row_begin = 0; sa.row_step = 1;
+  sa.gkeys = d_k; sa.gk_sig_stride = 0; sa.gk_scratch_off = total; sa.row_begin = 0; sa.row_step = 1;
   if (launch_select(sa, batch, 1, 0)) return -1;
   SFFTB_CUDA(cudaDeviceSynchronize());
   SFFTB_CUDA(cudaMemcpy(out_J, d_J, sizeof(int) * (long long)num * batch, cudaMemcpyDeviceToHost));

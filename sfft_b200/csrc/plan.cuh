@@ -89,6 +89,7 @@ struct PlanImpl {
   int version = 1;     // 1, 2, 3
   int n = 0, logn = 0, k = 0;
   int device = 0;
+  int flags = 0;       // the fftw_optimization word the plan was made with
   cudaStream_t own_stream = nullptr, stream = nullptr;
   PlanV12 v12;
   PlanV3 *v3 = nullptr;
@@ -100,7 +101,7 @@ struct PlanImpl {
 };
 
 // plan_v12.cu
-int v12_derive(PlanImpl *p, int n, int k, int with_comb);
+int v12_derive(PlanImpl *p, int n, int k, int with_comb, int tuned_by_k);
 int v12_build(PlanImpl *p);
 int v12_ensure_capacity(PlanImpl *p, int nsig);
 void v12_free(PlanImpl *p);

@@ -379,10 +379,40 @@ int build_window(int logn, WindowWork *ww, const Twiddles &twn, cudaStream_t st)
 // Build `count` filters of one plan together: filters that share (lobefrac, tolerance)
 // share the window, its n-point spectrum and the phase ramp (only the boxcar width differs,
 // the default for k > 50: src/sfft.cc:306-314), and all sequential chains run concurrently.
+static thread_local PresetFilters g_preset;
+void set_preset_filters(const PresetFilters *preset) { g_preset = preset ? *preset : PresetFilters(); }
+
+// upload cached filters (sfftb_load_plan) after checking them against the plan's geometry
+static int upload_preset(int count, const FilterSpec *specs, DeviceFilter **outs, cudaStream_t st)
+{
+  const PresetFilters pre = g_preset;
+  g_preset = PresetFilters();
+  if (pre.count != count) { set_error("plan cache: filter count does not match this plan"); return -1; }
+  for (int f = 0; f < count; f++) {
+    const int w = sfftb_host_dolph_width(specs[f].lobefrac, specs[f].tolerance);
+    if (pre.w[f] != w || pre.fw_half[f] != specs[f].fw_half) {
+      set_error("plan cache: filter sizes do not match the plan derived from (n, k, version, flags)");
+      return -1;
+    }
+    DeviceFilter *o = outs[f];
+    o->w = w;
+    o->fw_half = specs[f].fw_half;
+    const long long len = 2ll * o->fw_half + 1;
+    SFFTB_CUDA(cudaMalloc(&o->time, sizeof(cplx) * w));
+    SFFTB_CUDA(cudaMalloc(&o->fwin, sizeof(cplx) * len));
+    SFFTB_CUDA(cudaMemcpyAsync(o->time, pre.time[f], sizeof(cplx) * w, cudaMemcpyHostToDevice, st));
+    SFFTB_CUDA(cudaMemcpyAsync(o->fwin, pre.fwin[f], sizeof(cplx) * len, cudaMemcpyHostToDevice, st));
+    if (filter_refresh(o, st)) return -1;
+  }
+  SFFTB_CUDA(cudaStreamSynchronize(st));
+  return 0;
+}
+
 int build_filters(int logn, int count, const FilterSpec *specs, DeviceFilter **outs, cudaStream_t st)
 {
   const long long n = 1ll << logn;
   if (count < 1 || count > 2) { set_error("build_filters: one or two filters per plan"); return -1; }
+  if (g_preset.count) return upload_preset(count, specs, outs, st);
   WindowWork win[2];
   int which_win[2] = {0, 0}, nwin = 0;
   for (int f = 0; f < count; f++) {

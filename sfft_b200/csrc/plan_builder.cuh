@@ -34,6 +34,14 @@ int build_filter(int logn, double lobefrac, double tolerance, int b, int fw_half
 // sequential chains of every filter run concurrently
 int build_filters(int logn, int count, const FilterSpec *specs, DeviceFilter **outs, cudaStream_t st);
 void free_filter(DeviceFilter *f);
+// Plan cache: the next build_filters() call on this thread uploads these host arrays instead
+// of running the builder (sizes must match what the specs derive).  Cleared by that call.
+struct PresetFilters {
+  int count = 0;
+  int w[2] = {0, 0}, fw_half[2] = {0, 0};
+  const cplx *time[2] = {nullptr, nullptr}, *fwin[2] = {nullptr, nullptr};
+};
+void set_preset_filters(const PresetFilters *preset);
 // recompute the derived tables after fwin changed (plan build, sfftb_set_filter)
 int filter_refresh(DeviceFilter *f, cudaStream_t st);
 

@@ -67,7 +67,7 @@ int mod_inverse(int a, int n)
 int mod_inverse_pub(int a, int n) { return mod_inverse(a, n); }
 int gcd_pub(int a, int b) { return gcd_ref(a, b); }
 
-int v12_derive(PlanImpl *p, int n_req, int k, int with_comb)
+int v12_derive(PlanImpl *p, int n_req, int k, int with_comb, int tuned_by_k)
 {
   PlanV12 &v = p->v12;
   // defaults, src/sfft.cc:306-314
@@ -75,9 +75,14 @@ int v12_derive(PlanImpl *p, int n_req, int k, int with_comb)
   int loc_loops = 4, est_loops = 16, threshold_loops = 3, comb_loops = 1;
   double tol_loc = 1.e-8, tol_est = 1.e-8;
   // src/sfft.cc:316-327: for k > 50 the by-K table is searched with n as the key
+  // -- the by-K table is keyed by k (parameters.cc:282-513, tuned at n = 2^22), so that
+  // lookup never matches and every k > 50 plan runs on the defaults above.  The reference's
+  // behaviour is the default here too; SFFTB_PLAN_TUNED_BY_K (include/sfft.h) opts in to the
+  // lookup by k the table was written for.
   const int by_k = (unsigned)k > 50 ? 1 : 0;
+  const int key = by_k && tuned_by_k ? k : n_req;
   for (const ParamRow &r : kParamRows) {
-    if (r.by_k == by_k && r.with_comb == with_comb && r.key == n_req) {
+    if (r.by_k == by_k && r.with_comb == with_comb && r.key == key) {
       Bcst_loc = r.Bcst_loc; Bcst_est = r.Bcst_est; Comb_cst = r.Comb_cst;
       loc_loops = r.loc_loops; est_loops = r.est_loops;
       threshold_loops = r.threshold_loops; comb_loops = r.comb_loops;
@@ -236,7 +241,7 @@ int v12_ensure_capacity(PlanImpl *p, int nsig)
   SFFTB_CUDA(cudaMalloc(&v.d_count, sizeof(int) * S));
   SFFTB_CUDA(cudaMalloc(&v.d_stage, sizeof(int) * S * v.ints_per_sig));
   long long gk = 0;
-  if (v.B_loc > 16384) gk = (long long)v.loops_loc * v.B_loc;
+  if (v.B_loc > 16384) gk = (long long)v.loops_loc * select_gkeys_per_row(v.B_loc);
   if (v.with_comb) {
     const int W = v.W_Comb, words = W >= 32 ? W / 32 : 1;
     SFFTB_CUDA(cudaMalloc(&v.d_comb_xs, sizeof(cplx) * S * v.Comb_loops * W));
@@ -245,7 +250,8 @@ int v12_ensure_capacity(PlanImpl *p, int nsig)
     SFFTB_CUDA(cudaMalloc(&v.d_appr_bm, sizeof(unsigned) * S * words));
     SFFTB_CUDA(cudaMalloc(&v.d_approved, sizeof(int) * S * W));
     SFFTB_CUDA(cudaMalloc(&v.d_num_comb, sizeof(int) * S));
-    if (W > 16384 && (long long)v.Comb_loops * W > gk) gk = (long long)v.Comb_loops * W;
+    if (W > 16384 && (long long)v.Comb_loops * select_gkeys_per_row(W) > gk)
+      gk = (long long)v.Comb_loops * select_gkeys_per_row(W);
     v.max_comb = (int)((long long)v.Comb_loops * num < W ? (long long)v.Comb_loops * num : W);
     if (v2_struct_supported(v.geom, ilog2((unsigned)W)) && !getenv("SFFTB_NO_V2_STRUCT")) {
       SFFTB_CUDA(cudaMalloc(&v.d_xt, sizeof(cplx) * S * v.x_samp_size));
@@ -349,6 +355,7 @@ static int v12_stage_comb(PlanImpl *p, const cplx *d_in, const unsigned long lon
   sa.J = v.d_comb_J; sa.J_sig_stride = (long long)v.Comb_loops * num;
   sa.bitmap = v.d_comb_bm; sa.bm_sig_stride = (long long)v.Comb_loops * words;
   sa.gkeys = W > 16384 ? v.d_gkeys : nullptr; sa.gk_sig_stride = v.gkeys_per_sig;
+  sa.gk_scratch_off = (long long)v.Comb_loops * W;
   sa.row_begin = 0; sa.row_step = 1;
   if (launch_select(sa, v.Comb_loops, nsig, st)) return -1;
   if (launch_comb_merge(v.d_comb_bm, v.Comb_loops, W, p->n / W, v.d_appr_bm, v.d_approved,
@@ -406,6 +413,7 @@ static int v12_stage_finish(PlanImpl *p, int nsig, int slice_rank, int slice_wor
   sa.J = v.d_J; sa.J_sig_stride = (long long)v.loops_loc * num;
   sa.bitmap = v.d_bitmap; sa.bm_sig_stride = (long long)v.loops_loc * words_loc;
   sa.gkeys = v.B_loc > 16384 ? v.d_gkeys : nullptr; sa.gk_sig_stride = v.gkeys_per_sig;
+  sa.gk_scratch_off = (long long)v.loops_loc * v.B_loc;
   sa.row_begin = 0; sa.row_step = 1;
   if (launch_select(sa, v.loops_loc, nsig, st)) return -1;
   timer_mark(p, "select");

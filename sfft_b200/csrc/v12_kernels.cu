@@ -264,6 +264,218 @@ select_kernel(SelectArgs a)
   for (int i = tid; i < words; i += kSelectThreads) bm[i] = bm_s[i];
 }
 
+// ---------------------------------------------------------------------------
+// Rows above 16384 buckets (a v2 Comb spectrum of 2^17 points, location rows of 2^15 at
+// n = 2^27): the same MSD radix select spread over B/1024 CTAs, one key per thread, as a
+// chain of small kernels -- eight digit passes (block histogram in shared memory, flushed to
+// a per-row global histogram; every CTA re-derives the prefix decided so far from the
+// earlier passes' histograms, so no "decide" kernels are needed), a count pass and a
+// placement pass.  One CTA doing all of it was 290 us at W = 2^17 (one SM's L2 bandwidth).
+// Scratch per row: [8][256] u32 histogram, then B/1024 packed (greater << 32 | equal) counts.
+// ---------------------------------------------------------------------------
+constexpr int kBigThreads = 1024;
+long long select_big_scratch(int B) { return 1024 + (B + kBigThreads - 1) / kBigThreads; }
+
+struct BigRow {
+  unsigned long long *keys;
+  unsigned *hist;               // [8][256]
+  unsigned long long *cnt;      // [G]
+};
+__device__ __forceinline__ BigRow big_row(const SelectArgs &a, int launched_row, int s)
+{
+  const int row = a.row_begin + launched_row * a.row_step;
+  const long long B = 1ll << a.logB;
+  unsigned long long *base = a.gkeys + (long long)s * a.gk_sig_stride;
+  unsigned long long *scr = base + a.gk_scratch_off + (long long)row * (1024 + (B + kBigThreads - 1) / kBigThreads);
+  BigRow r;
+  r.keys = base + (long long)row * B;
+  r.hist = reinterpret_cast<unsigned *>(scr);
+  r.cnt = scr + 1024;
+  return r;
+}
+
+// replay the decisions of digit passes [0, upto): the wanted key's prefix and its rank from
+// the top among the keys sharing it.  Executed by warp 0; result broadcast through shared memory.
+__device__ __forceinline__ void big_decide(const unsigned *hist, int upto, unsigned num,
+                                           unsigned long long *sh_prefix, unsigned *sh_K)
+{
+  const int lane = threadIdx.x & 31;
+  unsigned long long prefix = 0;
+  unsigned K = num + 1u;
+  for (int q = 0; q < upto; q++) {
+    // lane l owns bins 255-8l .. 248-8l, i.e. lanes ascend as keys descend
+    unsigned c8[8], tot = 0;
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+      c8[t] = hist[q * 256 + 255 - 8 * lane - t];
+      tot += c8[t];
+    }
+    unsigned incl = tot;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const unsigned v = __shfl_up_sync(0xffffffffu, incl, off);
+      if (lane >= off) incl += v;
+    }
+    const unsigned excl = incl - tot;
+    unsigned digit = 0, newK = 0;
+    const bool owner = excl < K && K <= incl;
+    if (owner) {
+      unsigned run = excl;
+#pragma unroll
+      for (int t = 0; t < 8; t++) {
+        if (newK == 0 && K <= run + c8[t]) { digit = 255u - 8u * lane - t; newK = K - run; }
+        run += c8[t];
+      }
+    }
+    const unsigned who = __ffs(__ballot_sync(0xffffffffu, owner)) - 1;
+    digit = __shfl_sync(0xffffffffu, digit, who);
+    K = __shfl_sync(0xffffffffu, newK, who);
+    prefix = (prefix << 8) | digit;
+  }
+  if (lane == 0) { *sh_prefix = prefix; *sh_K = K; }
+}
+
+__global__ void __launch_bounds__(kBigThreads)
+select_big_pass_kernel(SelectArgs a, int pass)
+{
+  __shared__ unsigned h[256];
+  __shared__ unsigned long long sh_prefix;
+  __shared__ unsigned sh_K;
+  const BigRow r = big_row(a, blockIdx.y, blockIdx.z);
+  const int i = blockIdx.x * kBigThreads + threadIdx.x;
+  const int tid = threadIdx.x;
+  if (tid < 256) h[tid] = 0;
+  unsigned long long key;
+  if (pass == 0) {
+    const int row = a.row_begin + blockIdx.y * a.row_step;
+    const cplx *__restrict__ src = a.xs + (long long)blockIdx.z * a.xs_stride + (long long)row * a.row_stride;
+    key = (unsigned long long)__double_as_longlong(cabs2_rn(src[i]));
+    r.keys[i] = key;
+  } else {
+    key = r.keys[i];
+    if (tid < 32) big_decide(r.hist, pass, (unsigned)a.num, &sh_prefix, &sh_K);
+  }
+  __syncthreads();
+  const int shift = 56 - 8 * pass;
+  if (pass == 0 || (key >> (shift + 8)) == sh_prefix) {
+    // aggregate equal digits inside the warp before touching shared memory
+    const unsigned d = (unsigned)((key >> shift) & 255ull);
+    const unsigned peers = __match_any_sync(__activemask(), d);
+    if ((int)(__ffs(peers) - 1) == (tid & 31)) atomicAdd(&h[d], (unsigned)__popc(peers));
+  }
+  __syncthreads();
+  if (tid < 256 && h[tid]) atomicAdd(&r.hist[pass * 256 + tid], h[tid]);
+}
+
+__global__ void __launch_bounds__(kBigThreads)
+select_big_count_kernel(SelectArgs a)
+{
+  __shared__ unsigned long long sh_prefix;
+  __shared__ unsigned sh_K;
+  __shared__ unsigned long long wsum[32];
+  const BigRow r = big_row(a, blockIdx.y, blockIdx.z);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned long long key = r.keys[blockIdx.x * kBigThreads + tid];
+  if (tid < 32) big_decide(r.hist, 8, (unsigned)a.num, &sh_prefix, &sh_K);
+  __syncthreads();
+  const unsigned long long cutoff = sh_prefix;
+  unsigned long long c = key > cutoff ? (1ull << 32) : (key == cutoff ? 1ull : 0ull);
+#pragma unroll
+  for (int off = 16; off; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+  if (lane == 0) wsum[warp] = c;
+  __syncthreads();
+  if (warp == 0) {
+    unsigned long long t = wsum[lane];
+#pragma unroll
+    for (int off = 16; off; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+    if (lane == 0) r.cnt[blockIdx.x] = t;
+  }
+}
+
+__global__ void __launch_bounds__(kBigThreads)
+select_big_place_kernel(SelectArgs a)
+{
+  __shared__ unsigned long long sh_prefix;
+  __shared__ unsigned sh_K;
+  __shared__ unsigned long long wsum[32];
+  __shared__ unsigned long long sh_base;
+  const BigRow r = big_row(a, blockIdx.y, blockIdx.z);
+  const int row = a.row_begin + blockIdx.y * a.row_step;
+  const int s = blockIdx.z;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int i = blockIdx.x * kBigThreads + tid;
+  const unsigned long long key = r.keys[i];
+  if (tid < 32) big_decide(r.hist, 8, (unsigned)a.num, &sh_prefix, &sh_K);
+  // counts of the CTAs before this one
+  if (warp == 1) {
+    unsigned long long t = 0;
+    for (int c = lane; c < (int)blockIdx.x; c += 32) t += r.cnt[c];
+#pragma unroll
+    for (int off = 16; off; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+    if (lane == 0) sh_base = t;
+  }
+  __syncthreads();
+  const unsigned long long cutoff = sh_prefix;
+  const unsigned need = sh_K - 1u;          // ties at the cutoff to admit, in index order
+  const bool f_gt = key > cutoff, f_eq = key == cutoff;
+  const unsigned long long mine = f_gt ? (1ull << 32) : (f_eq ? 1ull : 0ull);
+  unsigned long long incl = mine;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += v;
+  }
+  if (lane == 31) wsum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const unsigned long long t = wsum[lane];
+    unsigned long long sc = t;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const unsigned long long v = __shfl_up_sync(0xffffffffu, sc, off);
+      if (lane >= off) sc += v;
+    }
+    wsum[lane] = sc - t;
+  }
+  __syncthreads();
+  const unsigned long long before = sh_base + wsum[warp] + incl - mine;
+  const unsigned gt_b = (unsigned)(before >> 32), eq_b = (unsigned)(before & 0xffffffffu);
+  const bool take = f_gt || (f_eq && eq_b < need);
+  if (take) {
+    int *J = a.J + (long long)s * a.J_sig_stride + (long long)row * a.num;
+    J[gt_b + (eq_b < need ? eq_b : need)] = i;
+  }
+  // a warp covers 32 consecutive buckets = one bitmap word
+  const unsigned word = __ballot_sync(0xffffffffu, take);
+  if (lane == 0) {
+    const int words = 1 << (a.logB - 5);
+    a.bitmap[(long long)s * a.bm_sig_stride + (long long)row * words + (i >> 5)] = word;
+  }
+}
+
+__global__ void select_big_zero_kernel(SelectArgs a)
+{
+  const BigRow r = big_row(a, blockIdx.x, blockIdx.y);
+  for (int t = threadIdx.x; t < 8 * 256; t += blockDim.x) r.hist[t] = 0u;
+}
+
+static int launch_select_big(const SelectArgs &a, int nrows, int nsig, cudaStream_t st)
+{
+  const int B = 1 << a.logB;
+  const dim3 grid((unsigned)(B / kBigThreads), (unsigned)nrows, (unsigned)nsig);
+  select_big_zero_kernel<<<dim3((unsigned)nrows, (unsigned)nsig), 256, 0, st>>>(a);
+  SFFTB_LAUNCH_CHECK();
+  for (int pass = 0; pass < 8; pass++) {
+    select_big_pass_kernel<<<grid, kBigThreads, 0, st>>>(a, pass);
+    SFFTB_LAUNCH_CHECK();
+  }
+  select_big_count_kernel<<<grid, kBigThreads, 0, st>>>(a);
+  SFFTB_LAUNCH_CHECK();
+  select_big_place_kernel<<<grid, kBigThreads, 0, st>>>(a);
+  SFFTB_LAUNCH_CHECK();
+  return 0;
+}
+
 static size_t select_smem_bytes(int B, bool keys_in_smem)
 {
   const int words = B >= 32 ? B / 32 : 1;
@@ -276,9 +488,12 @@ int launch_select(const SelectArgs &a, int nrows, int nsig, cudaStream_t st)
 {
   if (nrows <= 0) return 0;
   const int B = 1 << a.logB;
-  if (!a.gkeys && B > kSelectSmemKeys) {
-    set_error("launch_select: rows above 16384 buckets need the global key scratch");
-    return -1;
+  if (B > kSelectSmemKeys) {
+    if (!a.gkeys) {
+      set_error("launch_select: rows above 16384 buckets need the global key scratch");
+      return -1;
+    }
+    return launch_select_big(a, nrows, nsig, st);
   }
   static bool attr_set = false;
   if (!attr_set) {

@@ -41,9 +41,14 @@ struct SelectArgs {
   int logB, num;
   int *J;          long long J_sig_stride;      // [S][rows][num]
   unsigned *bitmap; long long bm_sig_stride;    // [S][rows][max(1,B/32)]
-  unsigned long long *gkeys; long long gk_sig_stride;   // global key scratch when B > 16384
+  // rows above 16384 buckets: global scratch per signal = [rows_total * B keys]
+  // [rows_total * select_big_scratch(B) words of histogram/count scratch at gk_scratch_off]
+  unsigned long long *gkeys; long long gk_sig_stride; long long gk_scratch_off;
   int row_begin, row_step;
 };
+// 64-bit words of global scratch one row of B > 16384 buckets needs: keys, then work area
+long long select_big_scratch(int B);
+inline long long select_gkeys_per_row(int B) { return (long long)B + select_big_scratch(B); }
 
 struct VoteArgs {
   const int *perm;

@@ -17,6 +17,7 @@ from . import _lib
 # flags copied from fftw3.h (python/sfft/sfft.py:7-8)
 FFTW_MEASURE = 0
 FFTW_ESTIMATE = 1 << 6
+PLAN_TUNED_BY_K = 1 << 24      # include/sfft.h SFFTB_PLAN_TUNED_BY_K
 
 # python/sfft/sfft.py:10-31
 V1_V2_INPUT_PARAMETERS = [
@@ -49,7 +50,7 @@ class sfft:
     itself accepts any power-of-two n, so pass False to reach e.g. n=2^27."""
 
     def __init__(self, length=16384, sparsity=50, version=1, optimization=FFTW_ESTIMATE,
-                 strict_parameters=True):
+                 strict_parameters=True, tuned_by_k=False):
         if not isinstance(length, (int, np.integer)) or isinstance(length, bool):
             raise TypeError("length is not an integer")
         if not isinstance(sparsity, (int, np.integer)) or isinstance(sparsity, bool):
@@ -76,10 +77,34 @@ class sfft:
 
         self._L = _lib.load()
         # python/sfft/sfft.py:74: the binding always plans with FFTW_ESTIMATE
-        self.sfft_plan = self._L.sfft_make_plan(self.length, self.sparsity, self.version - 1,
-                                                FFTW_ESTIMATE)
+        # tuned_by_k: opt in to the by-k parameter lookup the reference's table was written
+        # for (include/sfft.h SFFTB_PLAN_TUNED_BY_K); off = the reference's behaviour
+        flags = FFTW_ESTIMATE | (PLAN_TUNED_BY_K if tuned_by_k else 0)
+        self.sfft_plan = self._L.sfft_make_plan(self.length, self.sparsity, self.version - 1, flags)
         if not self.sfft_plan:
             raise RuntimeError("sfft_make_plan failed: " + _lib.last_error())
+
+    # -- plan cache ------------------------------------------------------------
+    def save(self, path):
+        """Write (n, k, version, flags) and both filters to `path` (sfftb_save_plan)."""
+        if self._L.sfftb_save_plan(self.sfft_plan, str(path).encode()):
+            raise RuntimeError(_lib.last_error())
+
+    @classmethod
+    def load(cls, path):
+        """Re-create a saved plan without running the filter builder (sfftb_load_plan)."""
+        L = _lib.load()
+        plan = L.sfftb_load_plan(str(path).encode())
+        if not plan:
+            raise RuntimeError("sfftb_load_plan failed: " + _lib.last_error())
+        self = cls.__new__(cls)
+        self._L = L
+        self.sfft_plan = plan
+        self.length = int(plan.contents.n)
+        self.sparsity = int(plan.contents.k)
+        self.version = int(plan.contents.version) + 1
+        self.optimization = FFTW_ESTIMATE
+        return self
 
     # -- reference surface ---------------------------------------------------
     def execute(self, a):

@@ -128,3 +128,51 @@ def test_exec_many_device_batch_matches_single(oracle_mod):
         assert counts[i] == want.size and np.array_equal(loc[o], want)
         assert bits_equal(val[o], out[want])
     p.close(); op.free()
+
+
+def test_plan_cache_round_trip(tmp_path, oracle_mod):
+    """A plan re-created from its file is the same plan: same filters, same results, bit for
+    bit, for every version (include/sfft.h sfftb_save_plan / sfftb_load_plan)."""
+    import sfft_b200.sfft as m
+    for version, n, k in ((1, 1 << 16, 50), (2, 1 << 16, 50), (3, 1 << 16, 50)):
+        x, _ = oracle_mod.generate_input(n, k, 99)
+        p = m.sfft(n, k, version)
+        path = tmp_path / ("plan_v%d.bin" % version)
+        p.save(path)
+        q = m.sfft.load(path)
+        assert (q.length, q.sparsity, q.version) == (n, k, version)
+        for which in (0, 1):
+            ta, fa = p.get_filter(which)
+            tb, fb = q.get_filter(which)
+            assert bits_equal(ta, tb) and bits_equal(fa, fb)
+        oracle_mod.seed(17, 5)
+        a = p.execute(x)
+        oracle_mod.seed(17, 5)
+        b = q.execute(x)
+        assert bits_equal(a, b)
+        p.close(); q.close()
+    # a file that is not a plan is refused loudly
+    bad = tmp_path / "bad.bin"
+    bad.write_bytes(b"not a plan")
+    with pytest.raises(RuntimeError):
+        m.sfft.load(bad)
+
+
+def test_tuned_by_k_is_opt_in(oracle_mod):
+    """k > 50 plans run on the reference's defaults (its by-K lookup never matches,
+    src/sfft.cc:316-321) unless SFFTB_PLAN_TUNED_BY_K asks for the by-k row
+    (src/parameters.cc:282-513); either way the planted coefficients come back."""
+    import sfft_b200.sfft as m
+    n, k = 1 << 22, 100
+    x, xf = oracle_mod.generate_input(n, k, 7)
+    true = np.flatnonzero(xf)
+    p = m.sfft(n, k, 1)
+    q = m.sfft(n, k, 1, tuned_by_k=True)
+    ip, iq = p.info(), q.info()
+    assert (ip["loops_loc"], ip["loops_est"]) == (4, 16)            # the defaults, sfft.cc:306-314
+    assert (iq["loops_loc"], iq["loops_est"]) == (3, 12)            # parameters.cc by-K row for k = 100
+    for plan in (p, q):
+        oracle_mod.seed(17, 2)
+        out = plan.execute(x)
+        assert np.abs(out[true] - xf[true]).max() < 0.1             # verification.cc:39-56
+        plan.close()
