@@ -113,3 +113,26 @@ def test_batch_equals_single_at_c5_shape(oracle_mod):
         o = np.argsort(l, kind="stable")
         assert c == counts[i] and np.array_equal(l[o], batch[i][0]) and bits_equal(v[o], batch[i][1])
     p.close()
+
+
+def test_v2_batch_equals_single_at_c2_shape(oracle_mod):
+    """The fused v2 estimation (persistent CTAs, tiles claimed from a per-signal counter)
+    must give every signal of a batch exactly what it gets alone."""
+    n, k, num = 1 << 24, 1000, 3
+    p = make_plan(n, k, 2)
+    xs = torch.stack([planted_signal(n, k, 80 + i)[0] for i in range(num)])
+    oracle_mod.seed(17, 6)
+    draws = [p.draw() for _ in range(num)]
+    counts = p.execute_many_device(xs, draws)
+    batch = []
+    for i in range(num):
+        l, v = p.result(i)
+        o = np.argsort(l, kind="stable")
+        batch.append((l[o], v[o]))
+    for i in range(num):
+        c = p.execute_device(xs[i], draws[i])
+        l, v = p.result()
+        o = np.argsort(l, kind="stable")
+        assert c == counts[i] == l.size and np.unique(l).size == l.size
+        assert np.array_equal(l[o], batch[i][0]) and bits_equal(v[o], batch[i][1])
+    p.close()
