@@ -510,6 +510,7 @@ long long sfftb_debug_fetch(sfft_plan *plan, const char *what, void *dst, size_t
   const void *src = nullptr;
   long long bytes = 0;
   const std::string w(what);
+  if ((w == "J" || w == "bitmap" || w == "voted") && v12_locate_on_demand(p)) return -1;
   const int loops = v.geom.loops;
   if (w == "x_samp" || w == "x_sampt") { src = v.d_xs; bytes = sizeof(cplx) * v.x_samp_size; }
   else if (w == "J") { src = v.d_J; bytes = sizeof(int) * (long long)v.loops_loc * v.B_thresh; }

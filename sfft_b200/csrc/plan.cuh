@@ -70,6 +70,7 @@ struct PlanV12 {
   cudaEvent_t stage_ev[kStageSlots] = {nullptr};
   int stage_next = 0;
   int cur_nsig = 0;
+  bool locate_skipped = false;             // v2: J / bitmap / voted list not computed for the last transform
   // CUDA-graph replay of the single-signal transform: the kernel sequence is captured once;
   // per call only the staged draw and the signal pointer (read indirectly) change
   cudaGraphExec_t graph_exec = nullptr;
@@ -110,6 +111,7 @@ int v12_exec(PlanImpl *p, const cplx *d_in, long long stride, int nsig, const sf
 void v12_shard_loops(const PlanImpl *p, int rank, int world, int *begin, int *end);
 int v12_shard_bucketize(PlanImpl *p, const cplx *d_in, const sfftb_draw *draw, int rank, int world);
 int v12_shard_finish(PlanImpl *p, int rank, int world);
+int v12_locate_on_demand(PlanImpl *p);
 
 // timing helpers
 void timer_begin(PlanImpl *p);

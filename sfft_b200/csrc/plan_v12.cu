@@ -398,8 +398,8 @@ static int v12_stage_bucketize(PlanImpl *p, const cplx *d_in, const unsigned lon
   return 0;
 }
 
-// |.|^2 + top-2k per location loop (cf12.cc:278-302), voting (:304-323), estimation (:341-419)
-static int v12_stage_finish(PlanImpl *p, int nsig, int slice_rank, int slice_world)
+// |.|^2 + top-2k per location loop (cf12.cc:278-302) and voting (:304-323)
+static int v12_stage_locate(PlanImpl *p, int nsig)
 {
   PlanV12 &v = p->v12;
   cudaStream_t st = p->stream;
@@ -429,6 +429,40 @@ static int v12_stage_finish(PlanImpl *p, int nsig, int slice_rank, int slice_wor
   va.num = num; va.thresh = v.loops_thresh;
   if (launch_vote(g, va, nsig, st)) return -1;
   timer_mark(p, "vote");
+  v.locate_skipped = false;
+  return 0;
+}
+
+// v2 only: the selection/voting of the last transform was skipped (see v12_stage_finish);
+// run it now on the bucket spectra still in place (debug hooks that read J / the voted set)
+int v12_locate_on_demand(PlanImpl *p)
+{
+  PlanV12 &v = p->v12;
+  if (!v.locate_skipped) return 0;
+  const int nsig = v.cur_nsig > 0 ? v.cur_nsig : 1;
+  SFFTB_CUDA(cudaMemsetAsync(v.d_voted_count, 0, sizeof(int) * nsig, p->stream));
+  if (v12_stage_locate(p, nsig)) return -1;
+  SFFTB_CUDA(cudaStreamSynchronize(p->stream));
+  return 0;
+}
+
+// location (selection + voting), then estimation (cf12.cc:341-419)
+static int v12_stage_finish(PlanImpl *p, int nsig, int slice_rank, int slice_world)
+{
+  PlanV12 &v = p->v12;
+  cudaStream_t st = p->stream;
+  const LoopGeom &g = v.geom;
+  const int *d_perm = v.d_stage;
+  // v2 estimates the pre-filled list {jj*W + r : r approved} (cf12.cc:505-512); every voted
+  // location has an approved residue (cf12.cc:126-184), so it is in that list already and the
+  // reference's voting only appends duplicates that `ans[loc] = value` overwrites with the
+  // same bits.  The result is identical without it: skip selection and voting (7 % of a C2
+  // transform) unless a debug hook asks for their outputs.
+  if (v.with_comb) {
+    v.locate_skipped = true;
+  } else if (v12_stage_locate(p, nsig)) {
+    return -1;
+  }
 
   EstimateArgs ea;
   ea.perm = d_perm;
