@@ -176,3 +176,27 @@ def test_tuned_by_k_is_opt_in(oracle_mod):
         out = plan.execute(x)
         assert np.abs(out[true] - xf[true]).max() < 0.1             # verification.cc:39-56
         plan.close()
+
+
+@pytest.mark.parametrize("scale", [1e-60, 1e60])
+def test_v2_fused_estimation_outside_the_fast_division_band(oracle_mod, scale):
+    """Spectra outside [2^-160, 2^190) make the fused v2 estimation kernel redo its tiles
+    with real divisions (v12_kernels.cu: run flags -> `unsafe`); the result must still be
+    the oracle's, bit for bit."""
+    import sfft_b200.sfft as m
+    n, k = 1 << 20, 100
+    x, _ = oracle_mod.generate_input(n, k, 31)
+    x = x * scale
+    p = m.sfft(n, k, 2, strict_parameters=False)
+    op = oracle_mod.Plan(n, k, 2)
+    oracle_mod.seed(17, 9)
+    cnt = p.execute_device(torch.from_numpy(x).cuda(), None)
+    loc, val = p.result()
+    oracle_mod.seed(17, 9)
+    out = op.exec(x)
+    want = np.flatnonzero(out)
+    o = np.argsort(loc, kind="stable")
+    keep = val[o] != 0
+    assert np.array_equal(loc[o][keep], want)
+    assert bits_equal(val[o][keep], out[want])
+    p.close(); op.free()
