@@ -911,7 +911,7 @@ v2_regroup_kernel(LoopGeom g, const cplx *__restrict__ xs, cplx *__restrict__ xt
 struct V2TileParams {
   cplx f[32];          // filter response at this residue's in-bucket offset
   double2 dr[32];      // (|f|^2, RN(1/|f|^2))
-  uint2 pm[32];        // element of hit u: (pm.x + pm.y*u) mod T
+  uint2 pm[32];        // byte offset of hit u's element in its run: (pm.x + pm.y*u) mod 16T
   unsigned r;          // the tile's residue
   int unsafe;          // this tile must use real divisions
   unsigned chunk;      // first chunk claimed by the CTA
@@ -1076,7 +1076,7 @@ v2_fused_kernel(LoopGeom g, V2StructArgs a)
     const unsigned P = ((p_bucket >> p_logq) + p_m * c) & (unsigned)((1 << logNW) - 1);
     const unsigned beta = cls | ((P & ((1u << sbits) - 1u)) << p_logq);
     const unsigned run0 = p_off + (beta << logT);
-    prm.pm[pj] = make_uint2((P >> sbits) & (unsigned)(T - 1), p_m & (unsigned)(T - 1));
+    prm.pm[pj] = make_uint2(((P >> sbits) & (unsigned)(T - 1)) << 4, (p_m & (unsigned)(T - 1)) << 4);
     const int bad = __any_sync(param_mask, p_fbad || s_unsafe[run0 >> logT]);
     if (pj == 0) { prm.unsafe = bad; prm.tile = tile; }
     // the CTA's reads of the previous tile (generic proxy) precede this copy (async proxy)
@@ -1105,7 +1105,7 @@ v2_fused_kernel(LoopGeom g, V2StructArgs a)
       const uint2 pm = prm.pm[j];
       const cplx f = prm.f[j];
       const double2 dr = prm.dr[j];
-      const cplx sv = lds_cplx(stage0 + (unsigned)j * kRunBytes + (((pm.x + pm.y * u) & (unsigned)(T - 1)) << 4));
+      const cplx sv = lds_cplx(stage0 + (unsigned)j * kRunBytes + ((pm.x + pm.y * u) & (kRunBytes - 16u)));
       const double ac = __dmul_rn(sv.x, f.x), bd = __dmul_rn(sv.y, f.y);
       const double ad = __dmul_rn(sv.x, f.y), bc = __dmul_rn(sv.y, f.x);
       vr[j] = div_fast(__dadd_rn(ac, bd), dr.x, dr.y);                             // :388-398
@@ -1118,7 +1118,7 @@ v2_fused_kernel(LoopGeom g, V2StructArgs a)
         const uint2 pm = prm.pm[j];
         const cplx f = prm.f[j];
         const double den = prm.dr[j].x;
-        const cplx sv = v2_stage[j * T + ((pm.x + pm.y * u) & (unsigned)(T - 1))];
+        const cplx sv = v2_stage[j * T + (((pm.x + pm.y * u) >> 4) & (unsigned)(T - 1))];
         const double ac = __dmul_rn(sv.x, f.x), bd = __dmul_rn(sv.y, f.y);
         const double ad = __dmul_rn(sv.x, f.y), bc = __dmul_rn(sv.y, f.x);
         const double qr = __ddiv_rn(__dadd_rn(ac, bd), den), qi = __ddiv_rn(__dsub_rn(ad, bc), den);
