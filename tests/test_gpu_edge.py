@@ -200,3 +200,28 @@ def test_v2_fused_estimation_outside_the_fast_division_band(oracle_mod, scale):
     assert np.array_equal(loc[o][keep], want)
     assert bits_equal(val[o][keep], out[want])
     p.close(); op.free()
+
+
+def test_v2_fused_and_generic_estimation_agree(oracle_mod, monkeypatch):
+    """The fused v2 estimation kernel and the generic per-hit kernel (the fallback for shapes
+    the fused one does not cover; SFFTB_NO_V2_STRUCT=1 forces it) are two implementations of
+    cf12.cc:341-419 over the same pre-filled list: identical results, different order."""
+    import sfft_b200.sfft as m
+    n, k = 1 << 20, 100
+    x, _ = oracle_mod.generate_input(n, k, 5)
+    xd = torch.from_numpy(x).cuda()
+    fused = m.sfft(n, k, 2, strict_parameters=False)
+    monkeypatch.setenv("SFFTB_NO_V2_STRUCT", "1")
+    generic = m.sfft(n, k, 2, strict_parameters=False)
+    monkeypatch.delenv("SFFTB_NO_V2_STRUCT")
+    oracle_mod.seed(17, 11)
+    d = fused.draw()
+    res = []
+    for p in (fused, generic):
+        cnt = p.execute_device(xd, d)
+        loc, val = p.result()
+        assert cnt == loc.size
+        o = np.argsort(loc, kind="stable")
+        res.append((loc[o], val[o]))
+        p.close()
+    assert np.array_equal(res[0][0], res[1][0]) and bits_equal(res[0][1], res[1][1])
