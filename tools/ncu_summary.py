@@ -87,7 +87,7 @@ def launches(path):
     # sequential chains, torch's input synthesis and the legacy dense scatter run outside the
     # timed region): these shares are the ones to compare with bench.py's stage_ms
     xform = {nm: v for nm, v in agg.items()
-             if re.match(r"(gather_kernel|select_kernel|vote_kernel|estimate_|v2_|comb_|fft_pass_kernel<[01]>|"
+             if re.match(r"(gather_kernel|select_|vote_kernel|estimate_|v2_|comb_|fft_pass_kernel<[01]>|"
                          r"(<unnamed>::)?v3_)", nm)}
     xt = sum(us for _, us in xform.values())
     if xt > 0:
