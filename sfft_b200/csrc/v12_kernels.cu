@@ -295,10 +295,15 @@ __device__ __forceinline__ BigRow big_row(const SelectArgs &a, int launched_row,
 }
 
 // replay the decisions of digit passes [0, upto): the wanted key's prefix and its rank from
-// the top among the keys sharing it.  Executed by warp 0; result broadcast through shared memory.
-__device__ __forceinline__ void big_decide(const unsigned *hist, int upto, unsigned num,
-                                           unsigned long long *sh_prefix, unsigned *sh_K)
+// the top among the keys sharing it.  The whole CTA first copies those passes' global
+// histograms into shared memory (one round trip instead of `upto` dependent ones), then
+// warp 0 scans them; result broadcast through shared memory (caller syncs afterwards).
+__device__ __forceinline__ void big_decide(const unsigned *ghist, int upto, unsigned num,
+                                           unsigned *hist, unsigned long long *sh_prefix, unsigned *sh_K)
 {
+  for (int t = threadIdx.x; t < upto * 256; t += blockDim.x) hist[t] = ghist[t];
+  __syncthreads();
+  if (threadIdx.x >= 32) return;
   const int lane = threadIdx.x & 31;
   unsigned long long prefix = 0;
   unsigned K = num + 1u;
@@ -339,6 +344,7 @@ __global__ void __launch_bounds__(kBigThreads)
 select_big_pass_kernel(SelectArgs a, int pass)
 {
   __shared__ unsigned h[256];
+  __shared__ unsigned prev[8 * 256];
   __shared__ unsigned long long sh_prefix;
   __shared__ unsigned sh_K;
   const BigRow r = big_row(a, blockIdx.y, blockIdx.z);
@@ -353,7 +359,7 @@ select_big_pass_kernel(SelectArgs a, int pass)
     r.keys[i] = key;
   } else {
     key = r.keys[i];
-    if (tid < 32) big_decide(r.hist, pass, (unsigned)a.num, &sh_prefix, &sh_K);
+    big_decide(r.hist, pass, (unsigned)a.num, prev, &sh_prefix, &sh_K);
   }
   __syncthreads();
   const int shift = 56 - 8 * pass;
@@ -370,13 +376,14 @@ select_big_pass_kernel(SelectArgs a, int pass)
 __global__ void __launch_bounds__(kBigThreads)
 select_big_count_kernel(SelectArgs a)
 {
+  __shared__ unsigned prev[8 * 256];
   __shared__ unsigned long long sh_prefix;
   __shared__ unsigned sh_K;
   __shared__ unsigned long long wsum[32];
   const BigRow r = big_row(a, blockIdx.y, blockIdx.z);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const unsigned long long key = r.keys[blockIdx.x * kBigThreads + tid];
-  if (tid < 32) big_decide(r.hist, 8, (unsigned)a.num, &sh_prefix, &sh_K);
+  big_decide(r.hist, 8, (unsigned)a.num, prev, &sh_prefix, &sh_K);
   __syncthreads();
   const unsigned long long cutoff = sh_prefix;
   unsigned long long c = key > cutoff ? (1ull << 32) : (key == cutoff ? 1ull : 0ull);
@@ -395,6 +402,7 @@ select_big_count_kernel(SelectArgs a)
 __global__ void __launch_bounds__(kBigThreads)
 select_big_place_kernel(SelectArgs a)
 {
+  __shared__ unsigned prev[8 * 256];
   __shared__ unsigned long long sh_prefix;
   __shared__ unsigned sh_K;
   __shared__ unsigned long long wsum[32];
@@ -405,7 +413,6 @@ select_big_place_kernel(SelectArgs a)
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int i = blockIdx.x * kBigThreads + tid;
   const unsigned long long key = r.keys[i];
-  if (tid < 32) big_decide(r.hist, 8, (unsigned)a.num, &sh_prefix, &sh_K);
   // counts of the CTAs before this one
   if (warp == 1) {
     unsigned long long t = 0;
@@ -414,6 +421,7 @@ select_big_place_kernel(SelectArgs a)
     for (int off = 16; off; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
     if (lane == 0) sh_base = t;
   }
+  big_decide(r.hist, 8, (unsigned)a.num, prev, &sh_prefix, &sh_K);
   __syncthreads();
   const unsigned long long cutoff = sh_prefix;
   const unsigned need = sh_K - 1u;          // ties at the cutoff to admit, in index order
