@@ -158,6 +158,10 @@ void sfft_free_plan(sfft_plan *plan)
     if (p->version == 3) v3_free(p); else v12_free(p);
     cudaFree(p->d_in);
     cudaFree(p->d_out);
+    cudaFree(p->d_zero);
+    if (p->h_loc) cudaFreeHost(p->h_loc);
+    if (p->h_val) cudaFreeHost(p->h_val);
+    if (p->zero_stream) cudaStreamDestroy(p->zero_stream);
     if (p->timer.created)
       for (int i = 0; i <= kMaxStages; i++) cudaEventDestroy(p->timer.ev[i]);
     cudaStreamDestroy(p->own_stream);
@@ -175,16 +179,44 @@ static int ensure_io(PlanImpl *p, long long in_elems)
     SFFTB_CUDA(cudaMalloc(&p->d_in, sizeof(cplx) * in_elems));
     p->d_in_elems = in_elems;
   }
+  return 0;
+}
+
+static int ensure_dense_out(PlanImpl *p)
+{
   if (!p->d_out) SFFTB_CUDA(cudaMalloc(&p->d_out, sizeof(cplx) * (long long)p->n));
   return 0;
 }
 
+constexpr long long kHostScatterCap = 1ll << 18;   // coefficients the host scatters itself
+constexpr long long kZeroElems = 4ll << 20;         // 64 MiB of device zeros, copied repeatedly
+
+static int ensure_sparse_out(PlanImpl *p)
+{
+  if (p->d_zero) return 0;
+  p->zero_elems = p->n < kZeroElems ? p->n : kZeroElems;
+  SFFTB_CUDA(cudaStreamCreateWithFlags(&p->zero_stream, cudaStreamNonBlocking));
+  SFFTB_CUDA(cudaMalloc(&p->d_zero, sizeof(cplx) * p->zero_elems));
+  SFFTB_CUDA(cudaMemset(p->d_zero, 0, sizeof(cplx) * p->zero_elems));
+  SFFTB_CUDA(cudaHostAlloc(&p->h_loc, sizeof(int) * kHostScatterCap, cudaHostAllocDefault));
+  SFFTB_CUDA(cudaHostAlloc(&p->h_val, sizeof(cplx) * kHostScatterCap, cudaHostAllocDefault));
+  return 0;
+}
+
+// The legacy entry points (host arrays in, dense zero-filled host arrays out;
+// src/sfft.cc:119-147).  v1 and v3 return a handful of coefficients, so the dense output is
+// zeros plus a host-side scatter: the zeros are DMA-ed into `out` on a second stream WHILE
+// the input is DMA-ed in (PCIe is full duplex), and only the sparse list comes back after the
+// transform.  v2's result is dense (cf12.cc:505-512): it is densified on the device and
+// copied back whole.
 static int exec_host(sfft_plan *plan, int num, sfft_complex **in, sfft_complex **out)
 {
   PlanImpl *p = impl(plan);
   if (!p) { set_error("sfft_exec: null plan"); return -1; }
   if (bind_device(p)) return -1;
   const long long n = p->n;
+  const bool sparse_out = p->version != 2;
+  if (sparse_out && ensure_sparse_out(p)) return -1;
   // batch size bounded by ~4 GiB of staged input
   long long chunk = (4ll << 30) / (16 * n);
   if (chunk < 1) chunk = 1;
@@ -200,11 +232,28 @@ static int exec_host(sfft_plan *plan, int num, sfft_complex **in, sfft_complex *
       if (sfftb_draw_random(plan, &draws[(size_t)s])) return -1;
       SFFTB_CUDA(cudaMemcpyAsync(p->d_in + s * n, in[base + s], sizeof(cplx) * n,
                                  cudaMemcpyHostToDevice, p->stream));
+      if (sparse_out)
+        for (long long off = 0; off < n; off += p->zero_elems) {
+          const long long len = n - off < p->zero_elems ? n - off : p->zero_elems;
+          SFFTB_CUDA(cudaMemcpyAsync(reinterpret_cast<cplx *>(out[base + s]) + off, p->d_zero, sizeof(cplx) * len,
+                                     cudaMemcpyDeviceToHost, p->zero_stream));
+        }
     }
     sfftb_result res;
     if (sfftb_exec_many_device(plan, cnt, p->d_in, n, draws.data(), &res, nullptr, 0)) return -1;
+    if (sparse_out) SFFTB_CUDA(cudaStreamSynchronize(p->zero_stream));
     for (int s = 0; s < cnt; s++) {
-      if (sfftb_densify(plan, s, p->d_out)) return -1;
+      if (sparse_out) {
+        const long long c = sfftb_fetch_result(plan, s, p->h_loc, reinterpret_cast<sfft_complex *>(p->h_val),
+                                               kHostScatterCap);
+        if (c < 0) return -1;
+        if (c <= kHostScatterCap) {
+          cplx *o = reinterpret_cast<cplx *>(out[base + s]);
+          for (long long i = 0; i < c; i++) o[p->h_loc[i]] = p->h_val[i];            // sfft.cc:121-123, cf12.cc:413
+          continue;
+        }
+      }
+      if (ensure_dense_out(p) || sfftb_densify(plan, s, p->d_out)) return -1;
       SFFTB_CUDA(cudaMemcpyAsync(out[base + s], p->d_out, sizeof(cplx) * n, cudaMemcpyDeviceToHost,
                                  p->stream));
     }

@@ -97,6 +97,11 @@ struct PlanImpl {
   // legacy host-pointer path
   cplx *d_in = nullptr;   long long d_in_elems = 0;
   cplx *d_out = nullptr;
+  // legacy path, sparse results: zeros streamed to the caller's `out` while the input
+  // streams in, then the few coefficients scattered by the host
+  cudaStream_t zero_stream = nullptr;
+  cplx *d_zero = nullptr;  long long zero_elems = 0;
+  int *h_loc = nullptr;    cplx *h_val = nullptr;     // pinned, kHostScatterCap entries
   int last_nsig = 0;
   StageTimer timer;
 };
