@@ -94,3 +94,15 @@ def test_product_does_not_touch_the_oracle():
                 assert not re.search(r"""["'][^"'\n]*oracle[/_.][^"'\n]*["']""", text), path
     out = os.popen(f"ldd {os.path.join(pkg, 'libsfft.so')}").read()
     assert "oracle" not in out
+
+
+def test_plan_cache_refuses_missing_and_foreign_files(tmp_path):
+    """sfftb_load_plan fails loudly (NULL + message) before touching any device: no CUDA needed."""
+    from sfft_b200 import _lib
+    L = _lib.load()
+    assert not L.sfftb_load_plan(str(tmp_path / "nope.plan").encode())
+    assert "cannot open" in _lib.last_error()
+    bad = tmp_path / "foreign.plan"
+    bad.write_bytes(b"SFFTBPL0" + bytes(64))
+    assert not L.sfftb_load_plan(str(bad).encode())
+    assert "not a plan file" in _lib.last_error()
