@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <atomic>
 #include <string>
 
 namespace sfftb {
@@ -36,6 +37,20 @@ extern long long g_launches;
                __LINE__, cudaGetErrorString(e__));                                  \
       ::sfftb::set_error(buf__);                                                    \
       return -1;                                                                    \
+    }                                                                               \
+  } while (0)
+
+// Run `body` (kernel attribute setup) the first time this call site is reached on each
+// device: function attributes are per device, and a process may hold plans on several.
+#define SFFTB_ONCE_PER_DEVICE(body)                                                 \
+  do {                                                                              \
+    static std::atomic<unsigned long long> done__{0};                               \
+    int dev__ = 0;                                                                  \
+    cudaGetDevice(&dev__);                                                          \
+    const unsigned long long bit__ = 1ull << (dev__ & 63);                          \
+    if (!(done__.load(std::memory_order_acquire) & bit__)) {                        \
+      body;                                                                         \
+      done__.fetch_or(bit__, std::memory_order_release);                            \
     }                                                                               \
   } while (0)
 

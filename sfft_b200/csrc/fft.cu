@@ -229,14 +229,12 @@ int fft_dit_inplace_ex(cplx *base, int logN, int nfft, long long fft_stride, int
     const size_t tile_elems = (size_t)1 << (ns + logT);
     size_t smem = sizeof(cplx) * (tile_elems + (logT == 0 ? (tile_elems >> 3) : 0) + 2);
     if (tw && !tw_fine && s0 == 0) smem += sizeof(cplx) << ns;
-    static bool attr_set = false;
-    if (!attr_set) {
+    SFFTB_ONCE_PER_DEVICE({
       const int max_smem = (int)(sizeof(cplx) * ((2u << kMaxTileLog) + (1u << (kMaxTileLog - 3)) + 4));
       SFFTB_CUDA(cudaFuncSetAttribute(fft_pass_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
       SFFTB_CUDA(cudaFuncSetAttribute(fft_pass_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
       SFFTB_CUDA(cudaFuncSetAttribute(fft_pass_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
-      attr_set = true;
-    }
+    });
     if (tw && tw_fine)
       fft_pass_kernel<2><<<grid, kFftThreads, smem, st>>>(base, s0, ns, logT, fft_stride, sig_stride, tw,
                                                          tw_fine, log_twN, sign);

@@ -503,12 +503,8 @@ int launch_select(const SelectArgs &a, int nrows, int nsig, cudaStream_t st)
     }
     return launch_select_big(a, nrows, nsig, st);
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    SFFTB_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                    (int)select_smem_bytes(kSelectSmemKeys, true)));
-    attr_set = true;
-  }
+  SFFTB_ONCE_PER_DEVICE(SFFTB_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                        (int)select_smem_bytes(kSelectSmemKeys, true))));
   dim3 grid((unsigned)nrows, (unsigned)nsig);
   select_kernel<<<grid, kSelectThreads, select_smem_bytes(B, a.gkeys == nullptr), st>>>(a);
   SFFTB_LAUNCH_CHECK();
@@ -1194,12 +1190,8 @@ int launch_v2_struct(const LoopGeom &g, const V2StructArgs &a, int max_comb, int
   switch (g.loops) {
 #define SFFTB_V2F_CASE(N)                                                                         \
   case N: {                                                                                       \
-    static bool attr_set = false;                                                                 \
-    if (!attr_set) {                                                                              \
-      SFFTB_CUDA(cudaFuncSetAttribute(v2_fused_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, \
-                                      kV2MaxSmem));                                               \
-      attr_set = true;                                                                            \
-    }                                                                                             \
+    SFFTB_ONCE_PER_DEVICE(SFFTB_CUDA(cudaFuncSetAttribute(                                        \
+        v2_fused_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, kV2MaxSmem)));           \
     v2_fused_kernel<N><<<grid, T, smem, st>>>(g, a);                                              \
   } break;
     SFFTB_V2F_CASE(2) SFFTB_V2F_CASE(3) SFFTB_V2F_CASE(4) SFFTB_V2F_CASE(5) SFFTB_V2F_CASE(6)
