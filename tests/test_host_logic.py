@@ -106,3 +106,15 @@ def test_plan_cache_refuses_missing_and_foreign_files(tmp_path):
     bad.write_bytes(b"SFFTBPL0" + bytes(64))
     assert not L.sfftb_load_plan(str(bad).encode())
     assert "not a plan file" in _lib.last_error()
+
+
+def test_generated_median_networks_are_current(tmp_path):
+    """sfft_b200/csrc/median_networks.inc is what tools/gen_median_networks.py generates --
+    and generating it re-verifies every network (0/1 principle, exhaustively up to L = 20)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = tmp_path / "median_networks.inc"
+    subprocess.check_call([sys.executable, os.path.join(root, "tools", "gen_median_networks.py"), str(out)],
+                          stdout=subprocess.DEVNULL)
+    assert out.read_text() == open(os.path.join(root, "sfft_b200", "csrc", "median_networks.inc")).read()

@@ -198,7 +198,7 @@ def name(s, n):
     return f"v[{s}]" if s < n else f"t{s - n}"
 
 
-def main():
+def main(out_path=OUT):
     lines = ["// GENERATED by tools/gen_median_networks.py -- do not edit.\n",
              "// MedianNet<L>::run(v): v[(L-1)/2] of the ascending order of v[0..L), straight-line\n",
              "// compare-exchange / min / max operations on registers (see the generator for the\n",
@@ -254,8 +254,9 @@ def main():
         lines.append(f"    return {name(want, n)};\n  }}\n}};\n")
         print(n, tag, "compares", compares, "selects", selects, "| A", a[2], a[1], "| B", b[2], b[1])
     lines.append("#undef SFFTB_CSWAP\n#undef SFFTB_MIN\n#undef SFFTB_MAX\n")
-    open(OUT, "w").writelines(lines)
+    open(out_path, "w").writelines(lines)
 
 
 if __name__ == "__main__":
-    main()
+    import sys
+    main(sys.argv[1] if len(sys.argv) > 1 else OUT)
