@@ -6,7 +6,10 @@ import pytest
 
 from util import bits_equal, random_phase_spectrum_signal
 
-CASES = [(1, 8192, 50), (2, 8192, 50), (1, 32768, 50), (2, 65536, 50), (1, 131072, 70), (2, 262144, 50)]
+CASES = [(1, 8192, 50), (2, 8192, 50), (1, 32768, 50), (2, 65536, 50), (1, 131072, 70), (2, 262144, 50),
+         # k > 50: the by-K lookup misses and the defaults stand (sfft.cc:316-321); the shape class of
+         # BASELINE configs 2 and 5
+         (2, 131072, 100), (1, 1048576, 100), (2, 1048576, 100)]
 
 
 @pytest.mark.parametrize("version,n,k", CASES)
