@@ -171,21 +171,60 @@ long long sfftb_fetch_result(sfft_plan *plan, int which, int *loc, sfft_complex 
                              long long capacity);
 
 /* ---- multi-GPU sharding of ONE v1/v2 transform (one process per GPU) --------
+ * (reference: the loops of outer_loop, src/computefourier-1.0-2.0.cc:438-541, are
+ * independent until voting and again until the median)
  * The signal is resident on every GPU.  Rank r of `world` bucketises only its own
- * block of loops (gather + bucket FFT, the bandwidth-heavy part); ONE collective
- * then makes the bucket spectra complete everywhere -- the caller sums the buffer
- * returned by sfftb_shard_spectra() over ranks (rows a rank does not own are
- * zero, so the sum is exact), e.g. torch.distributed.all_reduce over NCCL/NVLink.
- * Selection and voting are then replicated (they are cheap and deterministic);
- * estimation covers every hit (v1) or this rank's slice of the pre-filled list
- * (v2, where that list is the bulk of the work).
+ * block of loops (gather + bucket FFT, the bandwidth-heavy part); one exchange then
+ * makes the bucket spectra complete everywhere.  Selection and voting are replicated
+ * (cheap and deterministic); estimation covers every hit (v1) or this rank's slice of
+ * the pre-filled list (v2, where that list is the bulk of the work; the result stays
+ * distributed: rank r holds entries [offset, offset+count) of the single-GPU list,
+ * see sfftb_shard_slice).
+ * The draw must be the same on every rank: pass the same sfftb_draw, or pass NULL and
+ * seed libc (srand / srand48) identically on every rank.
+ * v3 has no loop structure to shard: replicas only.
+ *
+ * (1) NVLink peer exchange -- the fast path.  Buffers are mapped across processes with
+ * CUDA IPC; ranks store their rows into their peers' buffers over NVLink/NVSwitch and
+ * signal with flags in peer memory.  No NCCL call, no host synchronisation; the whole
+ * transform replays from one CUDA graph per rank.
+ *
+ *   sfftb_shard_export(plan, &mine);            // every rank
+ *   <all-gather the sfftb_peer_handle structs (plain bytes) by any means>
+ *   sfftb_shard_attach(plan, rank, world, all); // then a barrier between the ranks
+ *   sfftb_shard_exec(plan, d_in, draw, &result, sync);   // any number of times
+ *   <barrier>  sfftb_shard_detach(plan);
+ *
+ * A peer that never arrives makes the waiting kernels give up after 4 s (counted in
+ * sfftb_shard_status) instead of hanging the GPU. */
+#define SFFTB_IPC_HANDLE_BYTES 64
+typedef struct sfftb_peer_handle {
+  unsigned char spectra[SFFTB_IPC_HANDLE_BYTES];   /* cudaIpcMemHandle_t of the bucket-spectra buffer */
+  unsigned char flags[SFFTB_IPC_HANDLE_BYTES];     /* cudaIpcMemHandle_t of the flag block */
+} sfftb_peer_handle;
+int sfftb_shard_export(sfft_plan *plan, sfftb_peer_handle *mine);
+int sfftb_shard_attach(sfft_plan *plan, int rank, int world, const sfftb_peer_handle *all);
+int sfftb_shard_detach(sfft_plan *plan);
+int sfftb_shard_exec(sfft_plan *plan, const void *d_in, const sfftb_draw *draw, sfftb_result *result,
+                     int sync);
+/* transforms completed since attach, and flag waits that timed out (must be 0) */
+int sfftb_shard_status(sfft_plan *plan, long long *epoch, long long *timeouts);
+/* the part of the single-GPU result list that `rank` of `world` produced in the last
+ * sharded transform: entries [offset, offset + count) of that list, in its order
+ * (v1: the whole list on every rank) */
+int sfftb_shard_slice(sfft_plan *plan, int rank, int world, long long *offset, long long *count);
+
+/* (2) caller-side collective -- the portable fallback.  The caller sums the buffer
+ * returned by sfftb_shard_spectra() over ranks (rows a rank does not own are zero, so
+ * the sum is exact), e.g. torch.distributed.all_reduce over NCCL:
  *
  *   sfftb_shard_bucketize(plan, d_in, draw, rank, world);
  *   sfftb_shard_spectra(plan, &ptr, &count);  all_reduce(ptr, count doubles, SUM);
  *   sfftb_shard_finish(plan, rank, world, &result, sync);
  *
- * `draw` must be the same on every rank (draw on rank 0 and broadcast, or seed
- * libc identically).  v3 has no loop structure to shard: replicas only. */
+ * All three run on the plan's stream (sfftb_set_stream): the collective must be ordered
+ * after bucketize and before finish on that stream.  The pointer returned by
+ * sfftb_shard_spectra is invalidated when a later batch call grows the plan's scratch. */
 int sfftb_shard_bucketize(sfft_plan *plan, const void *d_in, const sfftb_draw *draw, int rank,
                           int world);
 int sfftb_shard_spectra(sfft_plan *plan, void **d_spectra, long long *n_doubles);

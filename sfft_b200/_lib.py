@@ -45,6 +45,11 @@ class Draw(C.Structure):
     ]
 
 
+class PeerHandle(C.Structure):
+    """sfftb_peer_handle: two CUDA IPC memory handles (plain bytes)."""
+    _fields_ = [("spectra", C.c_ubyte * 64), ("flags", C.c_ubyte * 64)]
+
+
 class Result(C.Structure):
     _fields_ = [("d_loc", C.c_void_p), ("d_val", C.c_void_p), ("d_count", C.c_void_p),
                 ("count", C.c_longlong)]
@@ -77,6 +82,12 @@ SYMBOLS = {
     "sfftb_shard_spectra": (_ci, [_PP, C.POINTER(_vp), C.POINTER(_ll)]),
     "sfftb_shard_finish": (_ci, [_PP, _ci, _ci, C.POINTER(Result), _ci]),
     "sfftb_shard_loops": (_ci, [_PP, _ci, _ci, C.POINTER(_ci), C.POINTER(_ci)]),
+    "sfftb_shard_export": (_ci, [_PP, C.POINTER(PeerHandle)]),
+    "sfftb_shard_attach": (_ci, [_PP, _ci, _ci, C.POINTER(PeerHandle)]),
+    "sfftb_shard_detach": (_ci, [_PP]),
+    "sfftb_shard_exec": (_ci, [_PP, _vp, C.POINTER(Draw), C.POINTER(Result), _ci]),
+    "sfftb_shard_status": (_ci, [_PP, C.POINTER(_ll), C.POINTER(_ll)]),
+    "sfftb_shard_slice": (_ci, [_PP, _ci, _ci, C.POINTER(_ll), C.POINTER(_ll)]),
     "sfftb_filter_sizes": (_ci, [_PP, _ci, C.POINTER(_ci), C.POINTER(_ci)]),
     "sfftb_get_filter": (_ci, [_PP, _ci, _vp, _vp]),
     "sfftb_set_filter": (_ci, [_PP, _ci, _vp, _vp]),

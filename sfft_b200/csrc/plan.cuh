@@ -26,6 +26,27 @@ struct StageTimer {
   bool created = false;
 };
 
+// NVLink peer exchange of the sharded transform (shard.cu): every rank's bucket-spectra
+// buffer and a small flag block are mapped into every other rank through CUDA IPC; ranks
+// store their rows straight into their peers' buffers and signal with flags.
+constexpr int kMaxPeers = 16;
+// layout of the flag block (unsigned words)
+enum { SH_READY = 0, SH_DONE = kMaxPeers, SH_EPOCH = 2 * kMaxPeers, SH_ERR = 2 * kMaxPeers + 1,
+       SH_CTR = 2 * kMaxPeers + 8, SH_WORDS = 3 * kMaxPeers + 8 };
+struct ShardPeers {
+  bool attached = false;
+  int rank = 0, world = 1;
+  unsigned *d_flags = nullptr;                 // local flag block, IPC-exported
+  cplx *peer_xs[kMaxPeers] = {nullptr};        // [rank] = local d_xs
+  unsigned *peer_flags[kMaxPeers] = {nullptr}; // [rank] = local d_flags
+  void *opened[2 * kMaxPeers] = {nullptr};     // mappings to close on detach
+  int n_opened = 0;
+  cudaGraphExec_t graph_exec = nullptr;
+  cudaGraph_t graph = nullptr;
+  int graph_kernels = 0;
+  int plain_execs = 0;
+};
+
 struct PlanV12 {
   // ---- derived parameters (src/sfft.cc:298-353) ----
   int with_comb = 0;
@@ -82,6 +103,7 @@ struct PlanV12 {
   int plain_execs = 0;
   int graph_kernels = 0;                   // kernels in one transform (for the launch counter)
   long long *h_counts = nullptr;   // pinned
+  ShardPeers shard;
 };
 
 struct PlanV3;   // v3.cu
@@ -116,6 +138,13 @@ int v12_exec(PlanImpl *p, const cplx *d_in, long long stride, int nsig, const sf
 void v12_shard_loops(const PlanImpl *p, int rank, int world, int *begin, int *end);
 int v12_shard_bucketize(PlanImpl *p, const cplx *d_in, const sfftb_draw *draw, int rank, int world);
 int v12_shard_finish(PlanImpl *p, int rank, int world);
+int v12_shard_exec(PlanImpl *p, const cplx *d_in, const sfftb_draw *draw);
+int v12_shard_slice(PlanImpl *p, int rank, int world, long long *offset, long long *count);
+void v12_shard_release(PlanImpl *p);
+// shard.cu: the peer-exchange kernels
+int launch_shard_push(const ShardPeers &sh, long long elem_off, long long elem_cnt, cudaStream_t st);
+int launch_shard_wait_ready(const ShardPeers &sh, cudaStream_t st);
+int launch_shard_done(const ShardPeers &sh, cudaStream_t st);
 int v12_locate_on_demand(PlanImpl *p);
 
 // timing helpers

@@ -226,6 +226,12 @@ int v12_ensure_capacity(PlanImpl *p, int nsig)
 {
   PlanV12 &v = p->v12;
   if (nsig <= v.cap) return 0;
+  if (v.shard.attached || v.shard.d_flags) {
+    // peers hold mappings of d_xs (sfftb_shard_export / _attach): it must not move
+    set_error("this plan's buffers are exported to peer GPUs (sharded transform): batches larger than the "
+              "capacity at export time need sfftb_shard_detach first");
+    return -1;
+  }
   SFFTB_CUDA(cudaStreamSynchronize(p->stream));
   v12_free_scratch(v);
   const long long S = nsig;
@@ -268,9 +274,24 @@ int v12_ensure_capacity(PlanImpl *p, int nsig)
   return 0;
 }
 
+void v12_shard_release(PlanImpl *p)
+{
+  ShardPeers &sh = p->v12.shard;
+  if (sh.graph_exec) cudaGraphExecDestroy(sh.graph_exec);
+  if (sh.graph) cudaGraphDestroy(sh.graph);
+  sh.graph_exec = nullptr; sh.graph = nullptr;
+  for (int i = 0; i < sh.n_opened; i++) cudaIpcCloseMemHandle(sh.opened[i]);
+  sh.n_opened = 0;
+  cudaFree(sh.d_flags);
+  sh.d_flags = nullptr;
+  sh.attached = false;
+  sh.world = 1; sh.rank = 0;
+}
+
 void v12_free(PlanImpl *p)
 {
   PlanV12 &v = p->v12;
+  v12_shard_release(p);
   v12_free_scratch(v);
   free_filter(&v.filt[0]);
   free_filter(&v.filt[1]);
@@ -611,5 +632,111 @@ int v12_shard_bucketize(PlanImpl *p, const cplx *d_in, const sfftb_draw *draw, i
 }
 
 int v12_shard_finish(PlanImpl *p, int rank, int world) { return v12_stage_finish(p, 1, rank, world); }
+
+// ---- peer exchange (shard.cu): one sharded transform, every step on the plan's stream ----
+static int v12_shard_body(PlanImpl *p, const cplx *d_in, const unsigned long long *x_ind)
+{
+  PlanV12 &v = p->v12;
+  const ShardPeers &sh = v.shard;
+  int lb, le;
+  v12_shard_loops(p, sh.rank, sh.world, &lb, &le);
+  if (v12_stage_comb(p, d_in, x_ind, p->n, 1)) return -1;              // tiny; replicated on every rank
+  if (v12_stage_bucketize(p, d_in, x_ind, p->n, 1, lb, le)) return -1;
+  // rows of loops [lb, le) are one contiguous block of the spectra buffer (cf12.cc:228-230)
+  const long long off = lb < v.loops_loc ? (long long)lb * v.B_loc
+                                         : (long long)v.loops_loc * v.B_loc + (long long)(lb - v.loops_loc) * v.B_est;
+  const long long end = le < v.loops_loc ? (long long)le * v.B_loc
+                                         : (long long)v.loops_loc * v.B_loc + (long long)(le - v.loops_loc) * v.B_est;
+  if (launch_shard_push(sh, off, end - off, p->stream)) return -1;
+  if (launch_shard_wait_ready(sh, p->stream)) return -1;
+  timer_mark(p, "exchange");
+  if (v12_stage_finish(p, 1, sh.rank, sh.world)) return -1;
+  if (launch_shard_done(sh, p->stream)) return -1;
+  return 0;
+}
+
+int v12_shard_exec(PlanImpl *p, const cplx *d_in, const sfftb_draw *draw)
+{
+  PlanV12 &v = p->v12;
+  ShardPeers &sh = v.shard;
+  cudaStream_t st = p->stream;
+  if (sh.plain_execs < 1 || p->timer.enabled || !graphs_enabled()) {
+    // first transform launch by launch (lazy one-time kernel attributes are set there)
+    timer_begin(p);
+    const long long launches0 = g_launches;
+    if (v12_stage_draws(p, 1, draw)) return -1;
+    if (v12_shard_body(p, d_in, nullptr)) return -1;
+    sh.graph_kernels = (int)(g_launches - launches0);
+    sh.plain_execs++;
+    return 0;
+  }
+  if (!sh.graph_exec) {
+    if (!v.h_gstage) {
+      SFFTB_CUDA(cudaHostAlloc(&v.h_gstage, sizeof(int) * v.ints_per_sig, cudaHostAllocDefault));
+      SFFTB_CUDA(cudaHostAlloc(&v.h_gx, sizeof(unsigned long long), cudaHostAllocDefault));
+      SFFTB_CUDA(cudaMalloc(&v.d_gx, sizeof(unsigned long long)));
+      SFFTB_CUDA(cudaEventCreateWithFlags(&v.g_ev, cudaEventDisableTiming));
+    }
+    SFFTB_CUDA(cudaStreamSynchronize(st));
+    SFFTB_CUDA(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    int rc = 0;
+    if (cudaMemcpyAsync(v.d_stage, v.h_gstage, sizeof(int) * v.ints_per_sig, cudaMemcpyHostToDevice, st) != cudaSuccess) rc = -1;
+    if (cudaMemcpyAsync(v.d_gx, v.h_gx, sizeof(unsigned long long), cudaMemcpyHostToDevice, st) != cudaSuccess) rc = -1;
+    if (cudaEventRecordWithFlags(v.g_ev, st, cudaEventRecordExternal) != cudaSuccess) rc = -1;
+    if (cudaMemsetAsync(v.d_voted_count, 0, sizeof(int), st) != cudaSuccess) rc = -1;
+    if (!rc) rc = v12_shard_body(p, nullptr, v.d_gx);
+    cudaGraph_t g = nullptr;
+    const cudaError_t e = cudaStreamEndCapture(st, &g);
+    if (rc || e != cudaSuccess || !g) {
+      if (g) cudaGraphDestroy(g);
+      cudaGetLastError();
+      set_error("CUDA graph capture of the sharded transform failed");
+      return -1;
+    }
+    sh.graph = g;
+    SFFTB_CUDA(cudaGraphInstantiate(&sh.graph_exec, sh.graph, 0));
+  }
+  SFFTB_CUDA(cudaEventSynchronize(v.g_ev));      // previous replay has consumed the staging buffers
+  fill_stage(v, v.h_gstage, 1, draw);
+  *v.h_gx = (unsigned long long)(uintptr_t)d_in;
+  SFFTB_CUDA(cudaGraphLaunch(sh.graph_exec, st));
+  g_launches += sh.graph_kernels;
+  p->last_nsig = 1;
+  v.cur_nsig = 1;
+  return 0;
+}
+
+// Which part of the single-GPU result list rank `rank` of `world` produces, as (offset, count)
+// in that list's order.  v1: everything (estimation is replicated).  v2: a block of the
+// pre-filled list -- whole tiles when the structured estimation kernel is in use, else hits.
+// Needs the Comb result of the last transform (synchronises the stream).
+int v12_shard_slice(PlanImpl *p, int rank, int world, long long *offset, long long *count)
+{
+  PlanV12 &v = p->v12;
+  SFFTB_CUDA(cudaStreamSynchronize(p->stream));
+  if (!v.with_comb) {
+    int c = 0;
+    SFFTB_CUDA(cudaMemcpy(&c, v.d_voted_count, sizeof(int), cudaMemcpyDeviceToHost));
+    *offset = 0;
+    *count = c > v.max_voted ? v.max_voted : c;
+    return 0;
+  }
+  int nc = 0;
+  SFFTB_CUDA(cudaMemcpy(&nc, v.d_num_comb, sizeof(int), cudaMemcpyDeviceToHost));
+  const int logNW = p->logn - ilog2((unsigned)v.W_Comb);
+  if (v.d_xt) {
+    const int logT = v2_struct_log_tile(v.geom, ilog2((unsigned)v.W_Comb));
+    const long long tiles = (long long)nc << (logNW - logT);
+    const long long lo = tiles * rank / world, hi = tiles * (rank + 1) / world;
+    *offset = lo << logT;
+    *count = (hi - lo) << logT;
+  } else {
+    const long long total = (long long)nc << logNW;
+    const long long lo = total * rank / world, hi = total * (rank + 1) / world;
+    *offset = lo;
+    *count = hi - lo;
+  }
+  return 0;
+}
 
 }  // namespace sfftb

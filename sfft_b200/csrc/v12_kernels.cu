@@ -1005,7 +1005,7 @@ v2_fused_kernel(LoopGeom g, V2StructArgs a)
   const int nc = a.num_comb[sig];
   long long lo, hi;
   v2_slice(a, (long long)nc << sbits, lo, hi);
-  if (a.slice_count && blockIdx.x == 0 && threadIdx.x == 0) a.slice_count[0] = (int)((hi - lo) << logT);
+  if (a.slice_count && blockIdx.x == 0 && threadIdx.x == 0) a.slice_count[sig] = (int)((hi - lo) << logT);
   const unsigned u = threadIdx.x;
   const unsigned stage0 = (unsigned)__cvta_generic_to_shared(v2_stage);
   const unsigned full = (unsigned)__cvta_generic_to_shared(&bars[0]);

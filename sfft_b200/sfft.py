@@ -5,8 +5,8 @@ optimization)` / `.execute(a)`, same TypeError/ValueError validation
 (python/sfft/sfft.py:52-67), ported to Python 3 / NumPy 2 and bound to the
 B200-native libsfft.so.  On top of `execute` (host ndarray in, dense host ndarray
 out, as in the reference) the class exposes the device-resident path:
-`execute_sparse` (host in, sparse out) and `execute_device` (CUDA tensor in,
-sparse CUDA tensors out).
+`execute_device` / `execute_many_device` (CUDA tensor in, sparse result left on the
+device; `result()` copies it to the host, `result_device()` views it as CUDA tensors).
 """
 import ctypes as C
 
@@ -160,6 +160,7 @@ class sfft:
                                             1 if sync else 0)
         if rc:
             raise RuntimeError(_lib.last_error())
+        self._last = res
         return list(counts) if sync else None
 
     def result(self, which=0):
@@ -175,6 +176,28 @@ class sfft:
                                              min(cnt, cap))
             if got < 0:
                 raise RuntimeError(_lib.last_error())
+        return loc, val
+
+    def result_device(self, which=0):
+        """The same list as `result()`, left on the device: (int32[count], complex128[count])
+        torch tensors viewing the plan's own buffers -- valid until the next transform."""
+        import torch
+        cnt = self._L.sfftb_fetch_result(self.sfft_plan, which, None, None, 0)
+        if cnt < 0:
+            raise RuntimeError(_lib.last_error())
+        cap = self.info()["max_hits"]
+        res = self._last
+        dev = torch.device("cuda", self.info()["device"])
+
+        class _View:
+            def __init__(self, ptr, count, typestr):
+                self.__cuda_array_interface__ = {"shape": (int(count),), "typestr": typestr,
+                                                 "data": (int(ptr), False), "version": 2}
+        if cnt == 0:
+            return (torch.empty(0, dtype=torch.int32, device=dev),
+                    torch.empty(0, dtype=torch.complex128, device=dev))
+        loc = torch.as_tensor(_View(res.d_loc + 4 * which * cap, cnt, "<i4"), device=dev)
+        val = torch.as_tensor(_View(res.d_val + 16 * which * cap, cnt, "<c16"), device=dev)
         return loc, val
 
     def densify(self, out, which=0, sync=True):

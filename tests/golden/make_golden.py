@@ -23,7 +23,11 @@ from oracle import ref  # noqa: E402
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
-# (version, n, k, srand seed, srand48 seed for the input, srand48 seed before exec)
+# (version, n, k, srand seed, srand48 seed for the input, srand48 seed before exec[, AWGN std])
+# AWGN (src/utils.cc:250-275) continues the drand48 stream of the input generator, as
+# src/simulation.cc does.  The last three are BASELINE configs 3 and 4 at FULL size and a
+# mid-size case with config 4's noise level (std = sqrt(k / (2 * 10^(20 dB / 10))) = 1.5811);
+# they take minutes each (the reference's plan builder) and skip the digests of n-long arrays.
 CASES = [
     (1, 16384, 50, 17, 12345, 999),
     (2, 16384, 50, 17, 12345, 999),
@@ -32,7 +36,11 @@ CASES = [
     (2, 131072, 60, 17, 2024, 5),
     (3, 16384, 50, 17, 12345, 999),
     (3, 262144, 100, 17, 77, 3),
+    (1, 1 << 22, 500, 17, 606, 11, (500 / 200.0) ** 0.5),
+    (3, 1 << 26, 2000, 17, 12345, 999),
+    (1, 1 << 27, 500, 17, 12345, 999, (500 / 200.0) ** 0.5),
 ]
+BIG = 1 << 26
 
 
 def sha(a):
@@ -41,8 +49,12 @@ def sha(a):
 
 def one(case):
     if True:
-        (v, n, k, s, s48_in, s48_exec) = case
+        (v, n, k, s, s48_in, s48_exec) = case[:6]
+        std = case[6] if len(case) > 6 else None
         x, xf = ref.generate_input(n, k, s48_in)
+        snr = None
+        if std is not None:
+            snr = ref.lib().ref_awgn(x.ctypes.data, n, std)
         p = ref.RefPlan(n, k, v)
         p.seed(s, s48_exec)
         out = p.exec(x)
@@ -50,15 +62,25 @@ def one(case):
         rec = dict(version=v, n=n, k=k, srand=s, srand48_input=s48_in, srand48_exec=s48_exec,
                    loc=loc, val=out[loc], true_loc=np.flatnonzero(xf).astype(np.int32),
                    sha_x=sha(x), sha_out=sha(out))
+        if std is not None:
+            rec["awgn_std"] = std
+            rec["awgn_snr"] = snr
         for key, val in p.params.items():
             rec["param_" + key] = val
         if v in (1, 2):
             rec["permute_ai"] = p.permute().copy()
+            rec["sha_x_samp"] = sha(p.x_samp())
+        if n >= BIG and v in (1, 2):
+            rec["sha_time_loc"] = sha(p.filter_time(False))
+            rec["sha_time_est"] = sha(p.filter_time(True))
+        elif n >= BIG:
+            rec["sha_filtert1"] = sha(p.v3_filter(0))
+            rec["sha_filtert2"] = sha(p.v3_filter(2))
+        elif v in (1, 2):
             rec["sha_time_loc"] = sha(p.filter_time(False))
             rec["sha_time_est"] = sha(p.filter_time(True))
             rec["sha_freq_loc"] = sha(p.filter_freq(False))
             rec["sha_freq_est"] = sha(p.filter_freq(True))
-            rec["sha_x_samp"] = sha(p.x_samp())
             rec["sha_score"] = sha(p.score())
             # a few taps verbatim so a digest mismatch can be localised
             rec["time_loc_head"] = p.filter_time(False)[:16].copy()
@@ -67,7 +89,7 @@ def one(case):
         else:
             for i, nm in enumerate(("filtert1", "filterf1", "filtert2", "filterf2")):
                 rec["sha_" + nm] = sha(p.v3_filter(i))
-        name = f"ref_v{v}_n{n}_k{k}.npz"
+        name = f"ref_v{v}_n{n}_k{k}{'_noisy' if std is not None else ''}.npz"
         np.savez_compressed(os.path.join(HERE, name), **rec)
         print(name, "locs", loc.size, flush=True)
         # skip interpreter teardown: after a v3 exec the reference has already
@@ -80,14 +102,18 @@ def main():
     # perm_x (src/computefourier-3.0.cc:235 vs src/sfft.cc:497-498), which can
     # corrupt the heap of a long-lived process
     import subprocess
-    for i in range(len(CASES)):
-        rc = subprocess.call([sys.executable, os.path.abspath(__file__), str(i)])
+    which = [int(a) for a in sys.argv[2:]] if len(sys.argv) > 2 and sys.argv[1] == "--only" else range(len(CASES))
+    for i in which:
+        # allocations above 32 KiB go to their own mmap: the one-element overrun then lands in
+        # the mapping's page slack instead of the next heap chunk's header
+        env = dict(os.environ, MALLOC_MMAP_THRESHOLD_="32768")
+        rc = subprocess.call([sys.executable, os.path.abspath(__file__), str(i)], env=env)
         if rc != 0:
             print("case", CASES[i], "FAILED in the reference itself, rc", rc)
 
 
 if __name__ == "__main__":
-    if len(sys.argv) > 1:
+    if len(sys.argv) > 1 and sys.argv[1] != "--only":
         one(CASES[int(sys.argv[1])])
     else:
         main()

@@ -1,6 +1,8 @@
 """Multi-GPU paths on real devices (needs >= 2 GPUs; run with `gpurun --gpus 2`):
-the loop-sharded transform must reproduce the single-GPU result bit for bit, and the
-signal-partitioned batch must reproduce the per-signal results of one GPU."""
+the loop-sharded transform -- through the NVLink peer exchange and through the NCCL
+fallback -- must reproduce the single-GPU result bit for bit, and the signal-partitioned
+batch must reproduce the per-signal results of one GPU.  The same check runs inside
+`bench.py --gpus N` ("sharded_parity"), which is what the driver sees."""
 import os
 import sys
 
@@ -26,40 +28,41 @@ def _worker(rank, world, port, tmp):
 
     stream = torch.cuda.Stream()
     torch.cuda.set_stream(stream)
-    for version, n, k in ((1, 1 << 18, 100), (2, 1 << 17, 60), (1, 1 << 22, 50)):
-        x, _ = oracle.generate_input(n, k, 77)
-        xd = torch.from_numpy(x).cuda()
-        plan = m.sfft(n, k, version, strict_parameters=False)
-        plan.set_stream(stream.cuda_stream)
-        # reference result: the whole transform on this GPU alone, with a broadcast draw
-        oracle.seed(17, 5)
-        draw = sd.broadcast_draw(plan.draw() if rank == 0 else plan.draw(), 0)
-        cnt1 = plan.execute_device(xd, draw)
-        loc1, val1 = plan.result()
-        o = np.argsort(loc1, kind="stable")
-        loc1, val1 = loc1[o], val1[o]
-        # sharded over `world` GPUs
-        st = sd.ShardedTransform(plan)
-        lb, le = st.owned_loops()
-        assert (lb, le) == sd.partition(plan.info()["loops_loc"] + plan.info()["loops_est"], rank, world)
-        cnt = st.execute(xd, draw)
-        loc, val = plan.result()
-        if version == 1:
-            o = np.argsort(loc, kind="stable")
-            assert cnt == cnt1 and np.array_equal(loc[o], loc1)
-            assert val[o].tobytes() == val1.tobytes(), "sharded values must be bit-identical"
-        else:
-            # v2: this rank holds its slice of the pre-filled list, in list order
-            b, e = sd.partition(cnt1, rank, world)
-            assert cnt == e - b
-            full_loc, full_val = np.empty(cnt1, np.int32), np.empty(cnt1, np.complex128)
-            # rebuild the unsorted single-GPU list order to compare slices
-            cntx = plan.execute_device(xd, draw)
-            ul, uv = plan.result()
-            cnt = st.execute(xd, draw)
+    for exchange in ("peer", "nccl"):
+        for version, n, k in ((1, 1 << 18, 100), (2, 1 << 17, 60), (2, 1 << 20, 100), (1, 1 << 22, 50)):
+            x, _ = oracle.generate_input(n, k, 77)
+            xd = torch.from_numpy(x).cuda()
+            plan = m.sfft(n, k, version, strict_parameters=False)
+            st = sd.ShardedTransform(plan, exchange=exchange)
+            if exchange == "peer":
+                assert st.exchange == "peer", st.peer_error
+            lb, le = st.owned_loops()
+            assert (lb, le) == sd.partition(plan.info()["loops_loc"] + plan.info()["loops_est"], rank, world)
+            # every rank draws for itself from identically seeded libc state: no broadcast
+            st.seed(17, 5)
+            draws = [plan.draw() for _ in range(4)]
+            for d in draws:          # several transforms: plain first, then graph replays
+                ok, compared = sd.sharded_matches_single(plan, st, xd, d)
+                assert ok and compared > 0
+            # draw=None path: libc state advances identically on every rank
+            st.seed(17, 5)
+            cnt = st.execute(xd, None)
             loc, val = plan.result()
-            assert np.array_equal(loc, ul[b:e]) and val.tobytes() == uv[b:e].tobytes()
-        plan.close()
+            off, n_slice = st.slice()
+            st.seed(17, 5)
+            dist.barrier()
+            cnt1 = plan.execute_device(xd, None)
+            loc1, val1 = plan.result()
+            dist.barrier()
+            if version == 1:
+                o, o1 = np.argsort(loc, kind="stable"), np.argsort(loc1, kind="stable")
+                assert cnt == cnt1 and np.array_equal(loc[o], loc1[o1]) and val[o].tobytes() == val1[o1].tobytes()
+            else:
+                assert cnt == n_slice and np.array_equal(loc, loc1[off:off + n_slice])
+                assert val.tobytes() == val1[off:off + n_slice].tobytes()
+            assert st.status()[1] == 0, "a flag wait timed out"
+            st.close()
+            plan.close()
 
     # signal-partitioned batch
     n, k, total = 1 << 16, 50, 6
@@ -67,7 +70,7 @@ def _worker(rank, world, port, tmp):
     plan.set_stream(stream.cuda_stream)
     sigs = [oracle.generate_input(n, k, 200 + i)[0] for i in range(total)]
     oracle.seed(17, 3)
-    draws = [sd.broadcast_draw(plan.draw(), 0) for _ in range(total)]
+    draws = [plan.draw() for _ in range(total)]
     b, e = sd.partition(total, rank, world)
     local = torch.from_numpy(np.stack(sigs[b:e])).cuda()
     counts = sd.exec_many_sharded(plan, local, draws)
@@ -79,7 +82,7 @@ def _worker(rank, world, port, tmp):
     dist.destroy_process_group()
 
 
-def test_two_gpus_nccl(tmp_path):
+def test_two_gpus(tmp_path):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs")
     import torch.multiprocessing as mp

@@ -3,7 +3,7 @@ reference (tests/golden/*.npz, made by tests/golden/make_golden.py)."""
 import numpy as np
 import pytest
 
-from util import bits_equal, load_golden, sha
+from util import bits_equal, golden_input, load_golden, sha
 
 V12_CASES = [(1, 16384, 50), (2, 16384, 50), (1, 65536, 50), (1, 262144, 100), (2, 131072, 60)]
 
@@ -35,6 +35,26 @@ def test_oracle_matches_reference_golden_v12(oracle_mod, version, n, k):
     # (src/verification.cc:39-56: |ans - f| <= 0.1)
     true = g["true_loc"]
     assert np.all(np.abs(out[true] - xf[true]) <= 0.1)
+    p.free()
+
+
+def test_oracle_matches_reference_golden_noisy(oracle_mod):
+    """config 4's noise level (20 dB AWGN, std = sqrt(k/200), src/utils.cc:250-275) at
+    n = 2^22, k = 500: the restatement against the compiled reference, bit for bit."""
+    n, k = 1 << 22, 500
+    g = load_golden(1, n, k, noisy=True)
+    x, xf = golden_input(oracle_mod, g)
+    assert abs(10 * np.log10(float(g["awgn_snr"])) - 20.0) < 0.05
+    p = oracle_mod.Plan(n, k, 1)
+    assert sha(p.arr("time_loc")) == str(g["sha_time_loc"])
+    oracle_mod.seed(int(g["srand"]), int(g["srand48_exec"]))
+    out = p.exec(x)
+    assert np.array_equal(p.arr("ai"), g["permute_ai"])
+    assert sha(p.arr("x_samp")) == str(g["sha_x_samp"])
+    assert sha(p.arr("score")) == str(g["sha_score"])
+    loc = np.flatnonzero(out).astype(np.int32)
+    assert np.array_equal(loc, g["loc"]) and bits_equal(out[loc], g["val"])
+    assert np.all(np.abs(out[g["true_loc"]] - 1.0) <= 0.1)
     p.free()
 
 

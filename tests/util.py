@@ -12,9 +12,21 @@ def sha(a):
     return hashlib.sha256(np.ascontiguousarray(a).tobytes()).hexdigest()
 
 
-def load_golden(version, n, k):
-    path = os.path.join(GOLDEN_DIR, f"ref_v{version}_n{n}_k{k}.npz")
+def load_golden(version, n, k, noisy=False):
+    path = os.path.join(GOLDEN_DIR, f"ref_v{version}_n{n}_k{k}{'_noisy' if noisy else ''}.npz")
     return dict(np.load(path))
+
+
+def golden_input(oracle, g):
+    """The exact input a fixture was generated from: the reference's generator
+    (src/simulation.cc:104-111) and, for noisy fixtures, AWGN continuing the same drand48
+    stream (src/utils.cc:250-275).  Checked against the fixture's digest of x."""
+    n, k = int(g["n"]), int(g["k"])
+    x, xf = oracle.generate_input(n, k, int(g["srand48_input"]))
+    if "awgn_std" in g:
+        oracle.lib().orc_awgn(x.ctypes.data, n, float(g["awgn_std"]))
+    assert sha(x) == str(g["sha_x"]), "oracle-generated input differs from the fixture's"
+    return x, xf
 
 
 def bits_equal(a, b):
