@@ -54,6 +54,32 @@ def env_int(name, default):
 
 
 # --------------------------------------------------------------------------- #
+# synthetic inputs: the SAME bits for this engine and for the reference arm
+# --------------------------------------------------------------------------- #
+def host_signal(n, k, seed, snr_db=None):
+    """k unit spikes at random locations -> x = unnormalised inverse DFT (the reference's
+    generator, src/simulation.cc:104-111, with numpy's RNG/FFT; synthesis is outside every
+    timed region).  Noisy: complex AWGN of the reference's model (src/utils.cc:263-273),
+    std = sqrt(k / (2 * 10^(SNR/10))).  Deterministic in (n, k, seed): both arms of the
+    bench, in different processes, transform identical input bits."""
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    loc = rng.integers(0, n, k)
+    xf = np.zeros(n, dtype=np.complex128)
+    xf[loc] = 1.0
+    x = np.fft.ifft(xf) * n
+    if snr_db is not None:
+        std = (k / (2.0 * 10 ** (snr_db / 10.0))) ** 0.5
+        u = np.maximum(rng.random(n), 1e-300)
+        v = rng.random(n)
+        x = x + std * np.sqrt(-2 * np.log(u)) * np.exp(2j * np.pi * v)
+    return np.ascontiguousarray(x)
+
+
+SIGNAL_SEED = 1000          # signal i of a workload uses seed SIGNAL_SEED + i (rank r: + 100000 r)
+
+
+# --------------------------------------------------------------------------- #
 # clocks sampling (B200_PROFILING.md recipe)
 # --------------------------------------------------------------------------- #
 class ClockSampler:
@@ -128,15 +154,8 @@ def cpu_reference_run(workload, nsig, steps, warmup, budget_s=150.0):
     t0 = time.time()
     plan = ref.RefPlan(n, k, version, kind=kind, threads=cores)
     plan_s = time.time() - t0
-    xs = []
-    for i in range(nsig):
-        x, _ = ref.generate_input(n, k, 1000 + i, kind=kind)
-        xs.append(x)
-    if snr_db is not None:
-        import math
-        std = math.sqrt(k / (2.0 * 10 ** (snr_db / 10.0)))
-        for x in xs:
-            L.ref_awgn(x.ctypes.data, n, std)
+    # the very signals the GPU arm transforms (rank 0's first `nsig`)
+    xs = [host_signal(n, k, SIGNAL_SEED + i, snr_db) for i in range(nsig)]
 
     def one():
         plan.seed(17, 4711)
@@ -161,8 +180,9 @@ def cpu_reference_run(workload, nsig, steps, warmup, budget_s=150.0):
     return {
         "value": value, "unit": "Gsamples/s", "cores": cores, "kind": "reference",
         "sample": (f"{len(times)} full sfft_exec{'_many' if nsig > 1 else ''} call(s) of {desc}, "
-                   f"{nsig} signal(s), reference sources built -O3 -ffast-math -march=x86-64-v3 "
-                   f"-fopenmp -DNDEBUG over the oracle's radix-2 FFT shim (FFTW is not installable); "
+                   f"{nsig} signal(s), same input bits as the GPU arm; reference sources built -O3 -ffast-math "
+                   f"-march=x86-64-v3 (not -march=native: the binary is built on another host) -fopenmp "
+                   f"-DNDEBUG over the oracle's radix-2 FFT shim (FFTW is not installable); "
                    f"plan build {plan_s:.1f}s excluded"),
         "steps_timed": len(times), "ms_per_step": 1e3 * total / len(times),
         "cpu_model": _cpu_model(),
@@ -207,40 +227,196 @@ def run_reference_arm(args):
 # --------------------------------------------------------------------------- #
 # our arm
 # --------------------------------------------------------------------------- #
-def synth_signals(torch, n, k, count, seed, snr_db, device):
-    """k unit spikes at random locations -> x = unnormalised inverse DFT (the
-    reference's generator, src/simulation.cc:104-111, with torch's RNG/FFT for speed;
-    synthesis is outside every timed region)."""
+def stage_bytes(info, stage, count):
+    """Algorithmic bytes of one stage per transform (DESIGN.md 'Measurement'): what the stage
+    must read and write once, 16 B per complex double, 4 B per index."""
+    n, num = info["n"], 2 * info["k"]
+    xs = info["x_samp_size"]
+    if info["version"] == 3:
+        W, B1, B2 = info["W_Man"], info["B_g1"], info["B_g2"]
+        slots = 2 * (W + B1 + B2)
+        if stage == "bucketise":      # samples + taps read, bucket arrays written
+            return 16 * info["gather_samples"] + info["gather_tap_bytes"] + 16 * slots
+        if stage == "bucket_fft":
+            return 2 * 16 * slots
+        if stage == "peel":           # every bucket read once + the recovered list written
+            return 16 * slots + 20 * count
+        if stage == "stage_draws":
+            return 32
+        return 0
+    loops = info["loops_loc"] + info["loops_est"]
+    if stage == "gather":
+        return 16 * (info["gather_samples"] - info["Comb_loops"] * info["W_Comb"] * (info["version"] == 2)) \
+            + info["gather_tap_bytes"] + 16 * xs
+    if stage == "estimate":
+        # read the bucket spectra once, write (loc:4 B, val:16 B) per recovered coefficient
+        return 16 * xs + 20 * count
+    if stage == "bucket_fft":
+        return 2 * 16 * xs
+    if stage == "select":             # location rows read, J + bitmap written
+        return 16 * info["loops_loc"] * info["B_loc"] + info["loops_loc"] * (4 * num + info["B_loc"] // 8)
+    if stage == "vote":               # J + bitmaps read, voted list written (upper bound: result count)
+        return info["loops_loc"] * (4 * num + info["B_loc"] // 8) + 4 * count
+    if stage == "comb":               # W samples read + spectrum written/read + approved list
+        W = info["W_Comb"] * info["Comb_loops"]
+        return 16 * W * 3 + 4 * num
+    if stage == "stage_draws":
+        return 4 * (2 * loops + info["Comb_loops"])
+    if stage == "exchange":
+        return 16 * xs
+    return 0
+
+
+# --------------------------------------------------------------------------- #
+# extras: the other BASELINE configs, at whatever N this run has
+# --------------------------------------------------------------------------- #
+def guarded(fn, *a):
+    """An extra must not sink the bench line."""
+    try:
+        return fn(*a)
+    except Exception as e:       # noqa: BLE001
+        import traceback
+        traceback.print_exc(file=sys.stderr)
+        return {"error": repr(e)}
+
+
+def timed_ms(ctx, fn, reps, warm=3):
+    """ms per call of fn(): CUDA events on the engine's stream, barrier + synchronize on both
+    sides, max over ranks."""
+    torch, dist = ctx["torch"], ctx["dist"]
+    for i in range(warm):
+        fn(i)
+    ctx["barrier"]()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(reps):
+        fn(i)
+    e1.record()
+    ctx["barrier"]()
+    t = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=ctx["dev"])
+    if ctx["world"] > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def device_signal(torch, n, k, seed, snr_db, dev):
+    """Device-side synthesis for the extras (never compared with the CPU arm)."""
     g = torch.Generator(device="cpu").manual_seed(seed)
-    out = []
-    for i in range(count):
-        loc = torch.randint(0, n, (k,), generator=g)
-        xf = torch.zeros(n, dtype=torch.complex128, device=device)
-        xf[loc.to(device)] = 1.0
-        x = torch.fft.ifft(xf) * n
-        if snr_db is not None:
-            std = (k / (2.0 * 10 ** (snr_db / 10.0))) ** 0.5
-            gd = torch.Generator(device=device).manual_seed(seed * 7919 + i)
-            u = torch.rand(n, generator=gd, device=device, dtype=torch.float64).clamp_min(1e-300)
-            v = torch.rand(n, generator=gd, device=device, dtype=torch.float64)
-            x = x + std * torch.sqrt(-2 * torch.log(u)) * torch.exp(2j * torch.pi * v)
-        out.append(x.contiguous())
-        del xf
+    loc = torch.randint(0, n, (k,), generator=g)
+    xf = torch.zeros(n, dtype=torch.complex128, device=dev)
+    xf[loc.to(dev)] = 1.0
+    x = torch.fft.ifft(xf) * n
+    del xf
+    if snr_db is not None:
+        std = (k / (2.0 * 10 ** (snr_db / 10.0))) ** 0.5
+        gd = torch.Generator(device=dev).manual_seed(seed * 7919 + 1)
+        u = torch.rand(n, generator=gd, device=dev, dtype=torch.float64).clamp_min(1e-300)
+        v = torch.rand(n, generator=gd, device=dev, dtype=torch.float64)
+        x = x + std * torch.sqrt(-2 * torch.log(u)) * torch.exp(2j * torch.pi * v)
+    return x.contiguous()
+
+
+def extra_loop_sharded(ctx, plan, x, what):
+    """ONE v1/v2 signal, loops block-partitioned over the ranks, bucket spectra completed by the
+    library's NVLink peer exchange (NCCL all-reduce timed beside it), every rank drawing the
+    same permutations from identically seeded libc.  Reports the single-GPU time of the same
+    transform on the same plan, and whether the sharded result equals it bit for bit."""
+    torch, dist, world = ctx["torch"], ctx["dist"], ctx["world"]
+    from sfft_b200 import dist as sd
+    reps = max(5, min(ctx["steps"], 20))
+    x_same = x
+    if world > 1:
+        x_same = x.clone()
+        dist.broadcast(x_same, src=0)               # every rank holds the same signal
+    single_ms = timed_ms(ctx, lambda i: plan.execute_device(x_same, None, sync=False), reps)
+    out = {"signals": 1, "what": what, "single_gpu_ms": single_ms, "n_gpus": world}
+    if world == 1:
+        out["ms_per_transform"] = single_ms
+        return out
+    for exchange in ("peer", "nccl"):
+        st = sd.ShardedTransform(plan, exchange=exchange)
+        st.seed(17, 4711)
+        parity, compared = sd.sharded_matches_single(plan, st, x_same, plan.draw())
+        parity2, _ = sd.sharded_matches_single(plan, st, x_same, plan.draw())      # graph replay
+        st.seed(17, 4712)
+        ms = timed_ms(ctx, lambda i: st.execute(x_same, None, sync=False), reps)
+        key = "" if exchange == "peer" else "nccl_"
+        out[key + "ms_per_transform"] = ms
+        out[key + "sharded_parity"] = bool(parity and parity2)
+        if exchange == "peer":
+            out["exchange"] = st.exchange
+            out["entries_compared_rank0"] = compared
+            out["flag_wait_timeouts"] = st.status()[1]
+            if st.peer_error:
+                out["peer_error"] = st.peer_error
+        st.close()
+    out["speedup_vs_single_gpu"] = single_ms / out["ms_per_transform"]
+    out["note"] = ("one signal resident on every rank; rank r gathers + FFTs its block of loops, stores its rows into "
+                   "every peer's spectra buffer over NVLink (CUDA IPC mappings) and flags; selection/voting replicated; "
+                   "v2 estimation sliced; whole transform incl. exchange replayed from one CUDA graph; max over ranks")
     return out
 
 
-def stage_bytes(info, stage, count):
-    """Algorithmic bytes of one stage per transform (DESIGN.md 'Measurement')."""
-    if stage == "gather":
-        return 16 * info["gather_samples"] + info["gather_tap_bytes"] + 16 * info["x_samp_size"]
-    if stage == "estimate":
-        # read the bucket spectra once, write (loc:4 B, val:16 B) per recovered coefficient
-        return 16 * info["x_samp_size"] + 20 * count
-    if stage == "bucket_fft":
-        return 2 * 16 * info["x_samp_size"]
-    if stage == "select":
-        return 16 * info["loops_loc"] * info["B_loc"]
-    return 0
+def extra_c4(ctx):
+    """BASELINE configs[3]: v1, n = 2^27, k = 500, 20 dB AWGN, loops sharded over all ranks."""
+    torch = ctx["torch"]
+    version, n, k, snr_db, desc = WORKLOADS["C4"]
+    plan = ctx["sfft_mod"].sfft(n, k, version, strict_parameters=False)
+    plan.set_stream(ctx["stream"].cuda_stream)
+    x = device_signal(torch, n, k, 4242, snr_db, ctx["dev"])
+    out = extra_loop_sharded(ctx, plan, x, desc)
+    out["gsamples_per_s"] = n / (out["ms_per_transform"] * 1e-3) / 1e9
+    plan.close()
+    del x
+    torch.cuda.empty_cache()
+    return out
+
+
+def extra_c5(ctx):
+    """BASELINE configs[4]: sfft_exec_many batch of 4096 signals (64 GiB), n = 2^20, k = 100,
+    block-partitioned over the ranks (strong scaling of the whole batch); no data-path collective."""
+    torch, world, rank, dev = ctx["torch"], ctx["world"], ctx["rank"], ctx["dev"]
+    version, n, k, _, _ = WORKLOADS["C5"]
+    total, chunk = 4096, 256
+    from sfft_b200 import dist as sd
+    b, e = sd.partition(total, rank, world)
+    plan = ctx["sfft_mod"].sfft(n, k, version, strict_parameters=False)
+    plan.set_stream(ctx["stream"].cuda_stream)
+    # this rank's signals, all resident in HBM (16 MiB each)
+    sig = torch.empty((e - b, n), dtype=torch.complex128, device=dev)
+    for i in range(e - b):
+        sig[i] = device_signal(torch, n, k, 50000 + b + i, None, dev)
+
+    def one_pass(_):
+        for c0 in range(0, e - b, chunk):
+            plan.execute_many_device(sig[c0:min(c0 + chunk, e - b)], None, sync=False)
+
+    ms = timed_ms(ctx, one_pass, 3, warm=1)
+    plan.close()
+    del sig
+    torch.cuda.empty_cache()
+    return {"signals_total": total, "signals_per_gpu": e - b, "n_gpus": world, "ms_per_batch": ms,
+            "gsamples_per_s": total * n / (ms * 1e-3) / 1e9, "scaling": "strong",
+            "note": "whole 4096-signal batch resident in HBM, partitioned over ranks, %d signals per launch; "
+                    "max over ranks" % chunk}
+
+
+def extra_c3(ctx):
+    """BASELINE configs[2]: v3, n = 2^26, k = 2000.  v3 does not shard (two adjacent time
+    shifts + sequential peeling): N independent replicas, each its own signal."""
+    torch, world, rank, dev = ctx["torch"], ctx["world"], ctx["rank"], ctx["dev"]
+    version, n, k, _, _ = WORKLOADS["C3"]
+    plan = ctx["sfft_mod"].sfft(n, k, version, strict_parameters=False)
+    plan.set_stream(ctx["stream"].cuda_stream)
+    x = device_signal(torch, n, k, 777 + rank, None, dev)
+    reps = max(5, min(ctx["steps"], 20))
+    ms = timed_ms(ctx, lambda i: plan.execute_device(x, None, sync=False), reps)
+    cnt = plan.execute_device(x, None, sync=True)
+    plan.close()
+    del x
+    torch.cuda.empty_cache()
+    return {"replicas": world, "ms_per_transform": ms, "gsamples_per_s": world * n / (ms * 1e-3) / 1e9,
+            "recovered_coefficients_rank0": int(cnt), "scaling": "weak (replicas only: v3 does not shard)"}
 
 
 def run_ours(args):
@@ -275,11 +451,13 @@ def run_ours(args):
     # smaller workloads additionally get an explicit L2 flush between steps
     batch = BATCH.get(args.workload, 1)
     nsig_rot = max(2, min(4, (1 << 28) // n)) if n <= (1 << 26) else 1
+    seed0 = SIGNAL_SEED + 100000 * rank
     if batch > 1:
         nsig_rot = 1
-        signals = [torch.stack(synth_signals(torch, n, k, batch, 1234 + rank, snr_db, dev))]
+        signals = [torch.stack([torch.from_numpy(host_signal(n, k, seed0 + i, snr_db)).to(dev)
+                                for i in range(batch)])]
     else:
-        signals = synth_signals(torch, n, k, nsig_rot, 1234 + rank, snr_db, dev)
+        signals = [torch.from_numpy(host_signal(n, k, seed0 + i, snr_db)).to(dev) for i in range(nsig_rot)]
     flush = None
     if batch * n * 16 < 256 * 1024 * 1024:
         flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
@@ -382,28 +560,19 @@ def run_ours(args):
     for ptr in h_in + h_out:
         L.sfft_free(ptr)
 
-    # ---- N > 1: ONE signal sharded over all ranks (loops split, one all-reduce) ----
-    sharded = None
-    if world > 1 and version in (1, 2):
-        from sfft_b200 import dist as sd
-        x_same = signals[0].clone()
-        dist.broadcast(x_same, src=0)               # every rank holds the same signal
-        st = sd.ShardedTransform(plan)
-        reps = max(3, min(args.steps, 10))
-        for _ in range(3):
-            st.execute(x_same, None, sync=False)
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(reps):
-            st.execute(x_same, None, sync=False)
-        e1.record()
-        barrier()
-        ts_ = torch.tensor([e0.elapsed_time(e1) / reps], dtype=torch.float64, device=dev)
-        dist.all_reduce(ts_, op=dist.ReduceOp.MAX)
-        sharded = {"ms_per_transform": float(ts_.item()), "signals": 1,
-                   "note": "one signal, loops block-partitioned over ranks, one NCCL all-reduce of "
-                           "the bucket spectra, draw broadcast from rank 0; max over ranks"}
+    # ---- what BASELINE.json names beyond configs[1] (every N; --no-extras skips) ----
+    extras = {}
+    ctx = dict(torch=torch, dist=dist, dev=dev, rank=rank, world=world, stream=stream, barrier=barrier,
+               sfft_mod=sfft_mod, steps=args.steps)
+    if not args.no_extras:
+        if version in (1, 2) and batch == 1:
+            # one signal of THIS workload with its loops sharded over all ranks
+            extras["loop_sharded_single_signal"] = guarded(
+                extra_loop_sharded, ctx, plan, signals[0], "this workload's signal")
+        if args.workload == "C2":
+            extras["c4_loop_sharded"] = guarded(extra_c4, ctx)
+            extras["c5_partitioned"] = guarded(extra_c5, ctx)
+            extras["c3_replicas"] = guarded(extra_c3, ctx)
 
     if rank == 0:
         peaks = {}
@@ -460,8 +629,7 @@ def run_ours(args):
             "wall_ms_per_step": 1e3 * t_wall / args.steps,
             "plan_ms": plan_ms,
         }
-        if sharded is not None:
-            line["loop_sharded_single_signal"] = sharded
+        line.update(extras)
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_reference_run(args.workload, min(batch, 8), 1, 0, budget_s=90.0)
@@ -481,6 +649,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the extra BASELINE configs (C4 loop-sharded, C5 partitioned, C3 replicas)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

@@ -117,6 +117,11 @@ sfft_plan *sfft_make_plan(int n, int k, sfft_version version, int fftw_optimizat
     return nullptr;
   }
   cudaGetLastError();   // drop any stale, non-sticky error left by the caller's earlier CUDA calls
+  if (const char *e = getenv("SFFTB_L2_FETCH")) {
+    // A/B knob (profiles/r02_gather_ab.md): device-wide L2 fetch granularity hint, 32 / 64 / 128 bytes
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)atoi(e));
+    cudaGetLastError();
+  }
   PlanImpl *p = new PlanImpl();
   if (cudaGetDevice(&p->device) != cudaSuccess) { delete p; return nullptr; }
   if (cudaStreamCreateWithFlags(&p->own_stream, cudaStreamNonBlocking) != cudaSuccess) {

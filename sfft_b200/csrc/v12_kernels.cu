@@ -1,4 +1,6 @@
 // v12_kernels.cu -- sm_100a kernels for sFFT v1/v2 (see v12_kernels.cuh).
+#include <stdlib.h>
+
 #include "v12_kernels.cuh"
 
 namespace sfftb {
@@ -82,7 +84,14 @@ int launch_gather(const LoopGeom &g, const GatherArgs &a, int nloops, int nsig, 
   dim3 grid((unsigned)ceil_div(1ll << maxlog, kGatherThreads), (unsigned)nloops, (unsigned)nsig);
   // fraction of the signal's samples the gathers of one transform read
   const double cover = ((double)g.loops_loc * g.w[0] + (double)(g.loops - g.loops_loc) * g.w[1]) / ((double)g.n_mask + 1.0);
-  if (cover < 0.25) gather_kernel<true><<<grid, kGatherThreads, 0, st>>>(g, a);
+  // SFFTB_GATHER_FILL=64|128 overrides the choice (A/B measurements, profiles/r02_gather_ab.md)
+  static int forced = -1;
+  if (forced < 0) {
+    const char *e = getenv("SFFTB_GATHER_FILL");
+    forced = e ? atoi(e) : 0;
+  }
+  const bool sparse = forced == 64 ? true : (forced == 128 ? false : cover < 0.25);
+  if (sparse) gather_kernel<true><<<grid, kGatherThreads, 0, st>>>(g, a);
   else gather_kernel<false><<<grid, kGatherThreads, 0, st>>>(g, a);
   SFFTB_LAUNCH_CHECK();
   return 0;

@@ -4,6 +4,7 @@ What is checked without a GPU: the block partitions cover every signal / loop / 
 exactly once; a draw made on rank 0 reaches rank 1 byte for byte; summing per-rank
 bucket-spectra buffers whose rows are disjoint reproduces the full array exactly
 (this is the one collective of the loop-sharded transform)."""
+import ctypes as C
 import os
 import sys
 
@@ -36,6 +37,11 @@ def _worker(rank, world, port, tmp):
         d.v3_b = 5
     got = sd.broadcast_draw(d, 0)
     assert got.loops == 20 and got.a[7] == 15 and got.ai[19] == 1019 and got.comb_offset[0] == 77 and got.v3_b == 5
+
+    # 1b. the peer-exchange handles (plain bytes) reach every rank in rank order
+    blobs = sd.all_gather_bytes(bytes([rank + 1]) * 128)
+    assert [b[0] for b in blobs] == list(range(1, world + 1)) and all(len(b) == 128 for b in blobs)
+    assert C.sizeof(_lib.PeerHandle) == 128
 
     # 2. loop-sharded bucket spectra assemble exactly: each rank fills only its own loops
     n, k = 16384, 50
