@@ -25,74 +25,113 @@ __device__ __forceinline__ long long loop_offset(const LoopGeom &g, int j)
 // while the taps stream coalesced and stay in L2 across loops.
 // ---------------------------------------------------------------------------
 constexpr int kGatherThreads = 256;
-constexpr int kGatherUnroll = 8;
+constexpr int kGatherUnroll = 8;        // independent sample loads a thread keeps in flight
 
-// SPARSE: the loops together touch only a small fraction of the signal, so a 128-byte
-// line fill mostly fetches samples nobody will read: ask for 64-byte fills.
-template <bool SPARSE>
+// Work item = 32 consecutive buckets of one (loop, signal): one warp.  CTAs are persistent (as
+// many as are resident at once) and warps stride over the items, so every SM gets the same
+// number of items whatever the shape -- a grid of one CTA per 256 buckets left the last wave
+// of C2 (1280 CTAs on 592 slots) running on a sixth of the machine.
+// FILL64: ask L2 for 64-byte fills around a sample instead of the whole 128-byte line; the
+// neighbours of a permuted sample are not wanted soon (halves the DRAM traffic, same or
+// better time at every BASELINE shape: profiles/r02_gather_ab.md).
+template <bool FILL64, int kGatherUnroll>
 __global__ void __launch_bounds__(kGatherThreads)
-gather_kernel(LoopGeom g, GatherArgs a)
+gather_kernel(LoopGeom g, GatherArgs a, int nloops, int nsig)
 {
-  const int j = a.loop_begin + blockIdx.y * a.loop_step;
-  const int s = blockIdx.z;
-  const bool est = j >= g.loops_loc;
-  const int logB = est ? g.logB[1] : g.logB[0];
-  const unsigned B = 1u << logB;
-  const unsigned b = blockIdx.x * kGatherThreads + threadIdx.x;
-  if (b >= B) return;
-
-  const int w = est ? g.w[1] : g.w[0];
-  const cplx *__restrict__ taps = est ? a.taps[1] : a.taps[0];
-  const cplx *__restrict__ x =
-      (a.x_indirect ? reinterpret_cast<const cplx *>(*a.x_indirect) : a.x) + (long long)s * a.x_stride;
-  const unsigned ai = (unsigned)a.perm[(long long)s * perm_stride(g.loops) + g.loops + j];
+  const int lane = threadIdx.x & 31;
+  const int warps_per_cta = kGatherThreads / 32;
   const unsigned mask = (unsigned)g.n_mask;
-
-  unsigned idx = (unsigned)(((unsigned long long)b * ai) & mask);
-  const unsigned stepB = (unsigned)(((unsigned long long)B * ai) & mask);
-
-  double acc_re = 0.0, acc_im = 0.0;
-  for (unsigned i = b; i < (unsigned)w; i += kGatherUnroll * B) {
-    cplx xv[kGatherUnroll], tv[kGatherUnroll];
-    unsigned id = idx;
-#pragma unroll
-    for (int u = 0; u < kGatherUnroll; u++) {
-      const unsigned ii = i + u * B;
-      xv[u] = SPARSE ? ldg_stream64(x + id) : ldg_stream(x + id);
-      tv[u] = __ldg(taps + (ii < (unsigned)w ? ii : 0u));
-      id = (id + stepB) & mask;
+  // items per loop differ between location and estimation loops: enumerate rows, then chunks
+  const int chunks0 = 1 << (g.logB[0] > 5 ? g.logB[0] - 5 : 0), chunks1 = 1 << (g.logB[1] > 5 ? g.logB[1] - 5 : 0);
+  const int lb = a.loop_begin, le = a.loop_begin + nloops;
+  const int nloc = (lb < g.loops_loc ? (le < g.loops_loc ? le : g.loops_loc) - lb : 0);   // location loops covered
+  const long long per_sig = (long long)nloc * chunks0 + (long long)(nloops - nloc) * chunks1;
+  const long long items = per_sig * nsig;
+  const cplx *__restrict__ xbase = a.x_indirect ? reinterpret_cast<const cplx *>(*a.x_indirect) : a.x;
+  for (long long it = (long long)blockIdx.x * warps_per_cta + (threadIdx.x >> 5); it < items;
+       it += (long long)gridDim.x * warps_per_cta) {
+    const int s = (int)(it / per_sig);
+    const long long r = it - (long long)s * per_sig;
+    int j, chunk;
+    if (r < (long long)nloc * chunks0) {
+      j = lb + (int)(r / chunks0);
+      chunk = (int)(r % chunks0);
+    } else {
+      const long long r1 = r - (long long)nloc * chunks0;
+      j = lb + nloc + (int)(r1 / chunks1);
+      chunk = (int)(r1 % chunks1);
     }
-    idx = id;
+    const bool est = j >= g.loops_loc;
+    const int logB = est ? g.logB[1] : g.logB[0];
+    const unsigned B = 1u << logB;
+    const unsigned b = (unsigned)chunk * 32u + (unsigned)lane;
+    if (b >= B) continue;
+    const int w = est ? g.w[1] : g.w[0];
+    const cplx *__restrict__ taps = est ? a.taps[1] : a.taps[0];
+    const cplx *__restrict__ x = xbase + (long long)s * a.x_stride;
+    const unsigned ai = (unsigned)a.perm[(long long)s * perm_stride(g.loops) + g.loops + j];
+
+    unsigned idx = (unsigned)(((unsigned long long)b * ai) & mask);
+    const unsigned stepB = (unsigned)(((unsigned long long)B * ai) & mask);
+
+    double acc_re = 0.0, acc_im = 0.0;
+    for (unsigned i = b; i < (unsigned)w; i += kGatherUnroll * B) {
+      cplx xv[kGatherUnroll], tv[kGatherUnroll];
+      unsigned id = idx;
 #pragma unroll
-    for (int u = 0; u < kGatherUnroll; u++) {
-      const unsigned ii = i + u * B;
-      if (ii < (unsigned)w) {
-        const cplx p = cmul_rn(xv[u], tv[u]);
-        acc_re = __dadd_rn(acc_re, p.x);
-        acc_im = __dadd_rn(acc_im, p.y);
+      for (int u = 0; u < kGatherUnroll; u++) {
+        const unsigned ii = i + u * B;
+        xv[u] = FILL64 ? ldg_stream64(x + id) : ldg_stream(x + id);
+        tv[u] = __ldg(taps + (ii < (unsigned)w ? ii : 0u));
+        id = (id + stepB) & mask;
+      }
+      idx = id;
+#pragma unroll
+      for (int u = 0; u < kGatherUnroll; u++) {
+        const unsigned ii = i + u * B;
+        if (ii < (unsigned)w) {
+          const cplx p = cmul_rn(xv[u], tv[u]);
+          acc_re = __dadd_rn(acc_re, p.x);
+          acc_im = __dadd_rn(acc_im, p.y);
+        }
       }
     }
+    cplx *xs = a.xs + (long long)s * g.x_samp_size + loop_offset(g, j);
+    xs[bitrev(b, logB)] = make_double2(acc_re, acc_im);
   }
-  cplx *xs = a.xs + (long long)s * g.x_samp_size + loop_offset(g, j);
-  xs[bitrev(b, logB)] = make_double2(acc_re, acc_im);
 }
 
 int launch_gather(const LoopGeom &g, const GatherArgs &a, int nloops, int nsig, cudaStream_t st)
 {
   if (nloops <= 0) return 0;
-  const int maxlog = g.logB[0] > g.logB[1] ? g.logB[0] : g.logB[1];
-  dim3 grid((unsigned)ceil_div(1ll << maxlog, kGatherThreads), (unsigned)nloops, (unsigned)nsig);
-  // fraction of the signal's samples the gathers of one transform read
-  const double cover = ((double)g.loops_loc * g.w[0] + (double)(g.loops - g.loops_loc) * g.w[1]) / ((double)g.n_mask + 1.0);
-  // SFFTB_GATHER_FILL=64|128 overrides the choice (A/B measurements, profiles/r02_gather_ab.md)
-  static int forced = -1;
+  long long items = 0;
+  for (int j = a.loop_begin; j < a.loop_begin + nloops; j++) {
+    const int logB = j >= g.loops_loc ? g.logB[1] : g.logB[0];
+    items += 1ll << (logB > 5 ? logB - 5 : 0);
+  }
+  items *= nsig;
+  // SFFTB_GATHER_FILL=64|128 and SFFTB_GATHER_UNROLL=4|8|12 override the defaults (A/B
+  // measurements, profiles/r02_gather_ab.md)
+  static int forced = -1, unroll = 0;
   if (forced < 0) {
     const char *e = getenv("SFFTB_GATHER_FILL");
     forced = e ? atoi(e) : 0;
+    const char *u = getenv("SFFTB_GATHER_UNROLL");
+    unroll = u ? atoi(u) : kGatherUnroll;
   }
-  const bool sparse = forced == 64 ? true : (forced == 128 ? false : cover < 0.25);
-  if (sparse) gather_kernel<true><<<grid, kGatherThreads, 0, st>>>(g, a);
-  else gather_kernel<false><<<grid, kGatherThreads, 0, st>>>(g, a);
+  typedef void (*kern_t)(LoopGeom, GatherArgs, int, int);
+  kern_t kern;
+  if (forced != 128) kern = unroll == 4 ? gather_kernel<true, 4> : (unroll == 12 ? gather_kernel<true, 12> : gather_kernel<true, 8>);
+  else kern = unroll == 4 ? gather_kernel<false, 4> : (unroll == 12 ? gather_kernel<false, 12> : gather_kernel<false, 8>);
+  // persistent CTAs: as many as are resident at once (registers decide)
+  int per_sm = 4;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kGatherThreads, 0) != cudaSuccess || per_sm < 1) {
+    cudaGetLastError();
+    per_sm = 4;
+  }
+  long long ctas = (items + kGatherThreads / 32 - 1) / (kGatherThreads / 32);
+  if (ctas > 148ll * per_sm) ctas = 148ll * per_sm;
+  kern<<<(unsigned)ctas, kGatherThreads, 0, st>>>(g, a, nloops, nsig);
   SFFTB_LAUNCH_CHECK();
   return 0;
 }
@@ -999,14 +1038,18 @@ __device__ __forceinline__ void mbar_arrive(unsigned bar)
 // the next tile's parameters and issue its copies; everybody else goes straight from the
 // divisions to the medians, so the copies fly under the medians and warps of one CTA
 // drift apart by up to a phase -- FP64-heavy divisions and ALU-heavy medians overlap.
-template <int L>
+// INTERLEAVE: the divisions of the imaginary parts are folded into the median network of the
+// real parts (MedianNet::run_with), so FP64-pipe work and ALU-pipe selects of ONE warp
+// overlap instead of alternating in phases; the per-tile parameters are double-buffered
+// because they are then still read after the stage has been released for the next copies.
+template <int L, bool INTERLEAVE>
 __global__ void __launch_bounds__(1 << kV2LogTile, 512 >> kV2LogTile)
 v2_fused_kernel(LoopGeom g, V2StructArgs a)
 {
   constexpr int logT = kV2LogTile, T = 1 << logT;
   constexpr unsigned kRunBytes = T * sizeof(cplx);
   extern __shared__ __align__(128) cplx v2_stage[];              // [L][T], then the run flags
-  __shared__ V2TileParams prm;
+  __shared__ V2TileParams prm2[INTERLEAVE ? 2 : 1];
   __shared__ __align__(8) unsigned long long bars[2];            // full, empty
   const int sig = blockIdx.y;
   const int logNW = g.logn - a.logW;
@@ -1032,7 +1075,7 @@ v2_fused_kernel(LoopGeom g, V2StructArgs a)
     mbar_init(full, L);
     mbar_init(empty, T / 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    prm.chunk = atomicAdd(ctr, 1u);
+    prm2[0].chunk = atomicAdd(ctr, 1u);
   }
   __syncthreads();
 
@@ -1050,11 +1093,14 @@ v2_fused_kernel(LoopGeom g, V2StructArgs a)
   int p_i = -1;
   unsigned p_bucket = 0;
   bool p_fbad = false;
-  long long p_tile = lo + (long long)prm.chunk * kV2Chunk;      // next tile to issue
+  long long p_tile = lo + (long long)prm2[0].chunk * kV2Chunk;      // next tile to issue
   long long p_chunk_end = p_tile + kV2Chunk;
   unsigned p_pending = 0;
+  int p_buf = 0;                                                 // parameter buffer of the next tile
   // writes the parameters of tile `p_tile` (or the end marker) and releases `full`
   auto issue_tile = [&]() {
+    V2TileParams &prm = prm2[p_buf];
+    if (INTERLEAVE) p_buf ^= 1;
     if (p_tile >= hi) {
       if (pj == 0) prm.tile = -1;
       mbar_arrive(full);
@@ -1108,6 +1154,7 @@ v2_fused_kernel(LoopGeom g, V2StructArgs a)
   unsigned parity = 0;
   while (true) {
     mbar_wait(full, parity);
+    const V2TileParams &prm = prm2[INTERLEAVE ? parity : 0];
     const long long tile = prm.tile;
     if (tile < 0) break;
     const unsigned r = prm.r;
@@ -1122,7 +1169,8 @@ v2_fused_kernel(LoopGeom g, V2StructArgs a)
       const double ac = __dmul_rn(sv.x, f.x), bd = __dmul_rn(sv.y, f.y);
       const double ad = __dmul_rn(sv.x, f.y), bc = __dmul_rn(sv.y, f.x);
       vr[j] = div_fast(__dadd_rn(ac, bd), dr.x, dr.y);                             // :388-398
-      vi[j] = div_fast(__dsub_rn(ad, bc), dr.x, dr.y);
+      // INTERLEAVE: only the numerator now, the division rides inside the first median
+      vi[j] = INTERLEAVE ? __dsub_rn(ad, bc) : div_fast(__dsub_rn(ad, bc), dr.x, dr.y);
     }
     if (unsafe) {
       // some input of this tile is zero or outside the band where div_fast is proven
@@ -1151,7 +1199,19 @@ v2_fused_kernel(LoopGeom g, V2StructArgs a)
     }
     parity ^= 1u;
 
-    const double re = MedianNet<L>::run(vr);
+    double re;
+    if (INTERLEAVE) {
+      // the parameters of this tile stay valid (double-buffered) although the stage is released
+      re = MedianNet<L>::run_with(vr, [&](auto step) {
+        constexpr int j = decltype(step)::value;
+        if (j < L && !unsafe) {
+          const double2 dr = prm.dr[j];
+          vi[j] = div_fast(vi[j], dr.x, dr.y);
+        }
+      });
+    } else {
+      re = MedianNet<L>::run(vr);
+    }
     const double im = MedianNet<L>::run(vi);
     const unsigned c = (unsigned)(tile & ((1ll << sbits) - 1));
     const unsigned jj = c + (u << sbits);
@@ -1196,12 +1256,22 @@ int launch_v2_struct(const LoopGeom &g, const V2StructArgs &a, int max_comb, int
   if (ctas < 1) ctas = 1;
   if (ctas > chunks) ctas = chunks;
   dim3 grid((unsigned)ctas, (unsigned)nsig);
+  static int interleave = -1;
+  if (interleave < 0) {
+    const char *e = getenv("SFFTB_V2_INTERLEAVE");
+    interleave = e ? atoi(e) : 0;
+  }
   switch (g.loops) {
 #define SFFTB_V2F_CASE(N)                                                                         \
   case N: {                                                                                       \
-    SFFTB_ONCE_PER_DEVICE(SFFTB_CUDA(cudaFuncSetAttribute(                                        \
-        v2_fused_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, kV2MaxSmem)));           \
-    v2_fused_kernel<N><<<grid, T, smem, st>>>(g, a);                                              \
+    SFFTB_ONCE_PER_DEVICE({                                                                       \
+      SFFTB_CUDA(cudaFuncSetAttribute(v2_fused_kernel<N, false>,                                  \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kV2MaxSmem));  \
+      SFFTB_CUDA(cudaFuncSetAttribute(v2_fused_kernel<N, true>,                                   \
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kV2MaxSmem));  \
+    });                                                                                           \
+    if (interleave) v2_fused_kernel<N, true><<<grid, T, smem, st>>>(g, a);                        \
+    else v2_fused_kernel<N, false><<<grid, T, smem, st>>>(g, a);                                  \
   } break;
     SFFTB_V2F_CASE(2) SFFTB_V2F_CASE(3) SFFTB_V2F_CASE(4) SFFTB_V2F_CASE(5) SFFTB_V2F_CASE(6)
     SFFTB_V2F_CASE(7) SFFTB_V2F_CASE(8) SFFTB_V2F_CASE(9) SFFTB_V2F_CASE(10) SFFTB_V2F_CASE(11)

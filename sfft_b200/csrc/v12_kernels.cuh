@@ -32,7 +32,7 @@ struct GatherArgs {
   const cplx *taps[2];
   const int *perm;
   cplx *xs;                 // [S][x_samp_size], written in bit-reversed bucket order
-  int loop_begin, loop_step;   // loops handled: loop_begin + blockIdx.y*loop_step (sharding)
+  int loop_begin, loop_step;   // loops handled: [loop_begin, loop_begin + nloops) (sharding); loop_step unused
 };
 
 struct SelectArgs {
