@@ -11,8 +11,11 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-OUT = os.path.join(HERE, "libsfft.so")
-BUILD = os.path.join(HERE, "build")
+# experiment builds: SFFTB_BUILD_VARIANT=t8 -> libsfft_t8.so with -DSFFTB_V2_LOG_TILE=8 (loaded via SFFTB_LIB)
+VARIANT = os.environ.get("SFFTB_BUILD_VARIANT", "")
+VARIANT_FLAGS = {"": [], "t8": ["-DSFFTB_V2_LOG_TILE=8"]}[VARIANT]
+OUT = os.path.join(HERE, "libsfft%s.so" % ("_" + VARIANT if VARIANT else ""))
+BUILD = os.path.join(HERE, "build" + ("_" + VARIANT if VARIANT else ""))
 
 CU_SOURCES = ["api.cu", "fft.cu", "plan_builder.cu", "plan_v12.cu", "v12_kernels.cu", "v3.cu", "shard.cu"]
 C_SOURCES = ["cheb_host.c"]
@@ -50,7 +53,7 @@ def build(force=False, verbose=False):
     procs = []
     for src in CU_SOURCES:
         obj = os.path.join(BUILD, src + ".o")
-        cmd = [NVCC] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [NVCC] + NVCC_FLAGS + VARIANT_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd))
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
@@ -73,7 +76,8 @@ def build(force=False, verbose=False):
     link = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", HOST_CXX,
             "-o", OUT] + objs + ["-lm"]
     subprocess.check_call(link)
-    build_tools()
+    if not VARIANT:
+        build_tools()
     return OUT
 
 

@@ -25,54 +25,42 @@ __device__ __forceinline__ long long loop_offset(const LoopGeom &g, int j)
 // while the taps stream coalesced and stay in L2 across loops.
 // ---------------------------------------------------------------------------
 constexpr int kGatherThreads = 256;
-constexpr int kGatherUnroll = 8;        // independent sample loads a thread keeps in flight
+constexpr int kGatherUnroll = 4;        // independent sample loads a thread keeps in flight (A/B: r02_gather_ab.md)
 
 // Work item = 32 consecutive buckets of one (loop, signal): one warp.  CTAs are persistent (as
 // many as are resident at once) and warps stride over the items, so every SM gets the same
 // number of items whatever the shape -- a grid of one CTA per 256 buckets left the last wave
-// of C2 (1280 CTAs on 592 slots) running on a sixth of the machine.
+// of C2 (1280 CTAs on 592 slots) running on a sixth of the machine.  One launch covers rows of
+// ONE bucket count (location rows, or estimation rows), so an item number decodes with
+// shifts and one 32-bit division; a warp spends its time waiting for samples, not on that.
 // FILL64: ask L2 for 64-byte fills around a sample instead of the whole 128-byte line; the
 // neighbours of a permuted sample are not wanted soon (halves the DRAM traffic, same or
 // better time at every BASELINE shape: profiles/r02_gather_ab.md).
 template <bool FILL64, int kGatherUnroll>
 __global__ void __launch_bounds__(kGatherThreads)
-gather_kernel(LoopGeom g, GatherArgs a, int nloops, int nsig)
+gather_kernel(LoopGeom g, GatherArgs a, int row_begin, int nrows, int grp, unsigned items)
 {
   const int lane = threadIdx.x & 31;
-  const int warps_per_cta = kGatherThreads / 32;
+  const unsigned warps_per_cta = kGatherThreads / 32;
   const unsigned mask = (unsigned)g.n_mask;
-  // items per loop differ between location and estimation loops: enumerate rows, then chunks
-  const int chunks0 = 1 << (g.logB[0] > 5 ? g.logB[0] - 5 : 0), chunks1 = 1 << (g.logB[1] > 5 ? g.logB[1] - 5 : 0);
-  const int lb = a.loop_begin, le = a.loop_begin + nloops;
-  const int nloc = (lb < g.loops_loc ? (le < g.loops_loc ? le : g.loops_loc) - lb : 0);   // location loops covered
-  const long long per_sig = (long long)nloc * chunks0 + (long long)(nloops - nloc) * chunks1;
-  const long long items = per_sig * nsig;
+  const int logB = g.logB[grp];
+  const int lc = logB > 5 ? logB - 5 : 0;            // log2(items per row)
+  const unsigned B = 1u << logB;
   const cplx *__restrict__ xbase = a.x_indirect ? reinterpret_cast<const cplx *>(*a.x_indirect) : a.x;
-  for (long long it = (long long)blockIdx.x * warps_per_cta + (threadIdx.x >> 5); it < items;
-       it += (long long)gridDim.x * warps_per_cta) {
-    const int s = (int)(it / per_sig);
-    const long long r = it - (long long)s * per_sig;
-    int j, chunk;
-    if (r < (long long)nloc * chunks0) {
-      j = lb + (int)(r / chunks0);
-      chunk = (int)(r % chunks0);
-    } else {
-      const long long r1 = r - (long long)nloc * chunks0;
-      j = lb + nloc + (int)(r1 / chunks1);
-      chunk = (int)(r1 % chunks1);
-    }
-    const bool est = j >= g.loops_loc;
-    const int logB = est ? g.logB[1] : g.logB[0];
-    const unsigned B = 1u << logB;
-    const unsigned b = (unsigned)chunk * 32u + (unsigned)lane;
+  for (unsigned it = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); it < items; it += gridDim.x * warps_per_cta) {
+    const unsigned row = it >> lc, chunk = it & ((1u << lc) - 1u);
+    const unsigned s = row / (unsigned)nrows;
+    const int j = row_begin + (int)(row - s * (unsigned)nrows);
+    const unsigned b = chunk * 32u + (unsigned)lane;
     if (b >= B) continue;
-    const int w = est ? g.w[1] : g.w[0];
-    const cplx *__restrict__ taps = est ? a.taps[1] : a.taps[0];
+    const int est = j >= g.loops_loc ? 1 : 0;        // rows of both kinds share a launch when B_loc == B_est
+    const int w = g.w[est];
+    const cplx *__restrict__ taps = a.taps[est];
     const cplx *__restrict__ x = xbase + (long long)s * a.x_stride;
     const unsigned ai = (unsigned)a.perm[(long long)s * perm_stride(g.loops) + g.loops + j];
 
-    unsigned idx = (unsigned)(((unsigned long long)b * ai) & mask);
-    const unsigned stepB = (unsigned)(((unsigned long long)B * ai) & mask);
+    unsigned idx = (b * ai) & mask;                  // n is a power of two <= 2^31
+    const unsigned stepB = (B * ai) & mask;
 
     double acc_re = 0.0, acc_im = 0.0;
     for (unsigned i = b; i < (unsigned)w; i += kGatherUnroll * B) {
@@ -101,38 +89,132 @@ gather_kernel(LoopGeom g, GatherArgs a, int nloops, int nsig)
   }
 }
 
-int launch_gather(const LoopGeom &g, const GatherArgs &a, int nloops, int nsig, cudaStream_t st)
+// The same arithmetic on a plain grid: one CTA per 256 buckets of one (loop, signal), CTAs
+// handed out by the hardware scheduler.  Used where the grid is many waves deep (batches).
+template <bool FILL64, int kGatherUnroll>
+__global__ void __launch_bounds__(kGatherThreads)
+gather_grid_kernel(LoopGeom g, GatherArgs a)
 {
-  if (nloops <= 0) return 0;
-  long long items = 0;
-  for (int j = a.loop_begin; j < a.loop_begin + nloops; j++) {
-    const int logB = j >= g.loops_loc ? g.logB[1] : g.logB[0];
-    items += 1ll << (logB > 5 ? logB - 5 : 0);
+  const int j = a.loop_begin + blockIdx.y;
+  const int s = blockIdx.z;
+  const bool est = j >= g.loops_loc;
+  const int logB = est ? g.logB[1] : g.logB[0];
+  const unsigned B = 1u << logB;
+  const unsigned b = blockIdx.x * kGatherThreads + threadIdx.x;
+  if (b >= B) return;
+  const int w = est ? g.w[1] : g.w[0];
+  const cplx *__restrict__ taps = est ? a.taps[1] : a.taps[0];
+  const cplx *__restrict__ x =
+      (a.x_indirect ? reinterpret_cast<const cplx *>(*a.x_indirect) : a.x) + (long long)s * a.x_stride;
+  const unsigned ai = (unsigned)a.perm[(long long)s * perm_stride(g.loops) + g.loops + j];
+  const unsigned mask = (unsigned)g.n_mask;
+  unsigned idx = (b * ai) & mask;
+  const unsigned stepB = (B * ai) & mask;
+  double acc_re = 0.0, acc_im = 0.0;
+  for (unsigned i = b; i < (unsigned)w; i += kGatherUnroll * B) {
+    cplx xv[kGatherUnroll], tv[kGatherUnroll];
+    unsigned id = idx;
+#pragma unroll
+    for (int u = 0; u < kGatherUnroll; u++) {
+      const unsigned ii = i + u * B;
+      xv[u] = FILL64 ? ldg_stream64(x + id) : ldg_stream(x + id);
+      tv[u] = __ldg(taps + (ii < (unsigned)w ? ii : 0u));
+      id = (id + stepB) & mask;
+    }
+    idx = id;
+#pragma unroll
+    for (int u = 0; u < kGatherUnroll; u++) {
+      const unsigned ii = i + u * B;
+      if (ii < (unsigned)w) {
+        const cplx p = cmul_rn(xv[u], tv[u]);
+        acc_re = __dadd_rn(acc_re, p.x);
+        acc_im = __dadd_rn(acc_im, p.y);
+      }
+    }
   }
-  items *= nsig;
-  // SFFTB_GATHER_FILL=64|128 and SFFTB_GATHER_UNROLL=4|8|12 override the defaults (A/B
-  // measurements, profiles/r02_gather_ab.md)
-  static int forced = -1, unroll = 0;
-  if (forced < 0) {
-    const char *e = getenv("SFFTB_GATHER_FILL");
-    forced = e ? atoi(e) : 0;
-    const char *u = getenv("SFFTB_GATHER_UNROLL");
-    unroll = u ? atoi(u) : kGatherUnroll;
+  cplx *xs = a.xs + (long long)s * g.x_samp_size + loop_offset(g, j);
+  xs[bitrev(b, logB)] = make_double2(acc_re, acc_im);
+}
+
+// how a gather is launched; defaults by shape, every field overridable from the environment
+// while tuning (SFFTB_GATHER_MODE=grid|persist, SFFTB_GATHER_UNROLL=4|8, SFFTB_GATHER_CTAS=<per SM>,
+// SFFTB_GATHER_FILL=64|128; read at every launch so one process can sweep them)
+struct GatherTune {
+  bool persist;
+  int unroll;
+  int ctas_per_sm;     // persistent mode: cap on resident CTAs per SM (0: whatever fits)
+  bool fill64;
+};
+static GatherTune gather_tune(const LoopGeom &g, int nloops, int nsig)
+{
+  GatherTune t;
+  // waves of the plain grid: a shallow grid ends on a ragged last wave, which the persistent
+  // form avoids; a deep one (batches) is balanced already
+  const int maxlog = g.logB[0] > g.logB[1] ? g.logB[0] : g.logB[1];
+  const double waves = (double)ceil_div(1ll << maxlog, kGatherThreads) * nloops * nsig / (148.0 * 4);
+  t.persist = g.logB[0] == g.logB[1] && waves > 1.0 && waves < 3.0;
+  t.unroll = t.persist ? 4 : 8;
+  t.ctas_per_sm = 0;
+  t.fill64 = true;
+  if (getenv("SFFTB_TUNE")) {
+    if (const char *e = getenv("SFFTB_GATHER_MODE")) t.persist = e[0] == 'p';
+    if (const char *e = getenv("SFFTB_GATHER_UNROLL")) t.unroll = atoi(e) == 8 ? 8 : 4;
+    if (const char *e = getenv("SFFTB_GATHER_CTAS")) t.ctas_per_sm = atoi(e);
+    if (const char *e = getenv("SFFTB_GATHER_FILL")) t.fill64 = atoi(e) != 128;
   }
-  typedef void (*kern_t)(LoopGeom, GatherArgs, int, int);
+  return t;
+}
+
+// rows [row_begin, row_begin + nrows) of every signal, all with the same bucket count
+static int launch_gather_rows(const LoopGeom &g, const GatherArgs &a, const GatherTune &t, int row_begin, int nrows,
+                              int nsig, cudaStream_t st)
+{
+  if (nrows <= 0) return 0;
+  const int grp = row_begin >= g.loops_loc ? 1 : 0;
+  const int lc = g.logB[grp] > 5 ? g.logB[grp] - 5 : 0;
+  const long long items = ((long long)nrows * nsig) << lc;
+  if (items >= (1ll << 32)) { set_error("launch_gather: batch too large for one launch"); return -1; }
+  typedef void (*kern_t)(LoopGeom, GatherArgs, int, int, int, unsigned);
   kern_t kern;
-  if (forced != 128) kern = unroll == 4 ? gather_kernel<true, 4> : (unroll == 12 ? gather_kernel<true, 12> : gather_kernel<true, 8>);
-  else kern = unroll == 4 ? gather_kernel<false, 4> : (unroll == 12 ? gather_kernel<false, 12> : gather_kernel<false, 8>);
-  // persistent CTAs: as many as are resident at once (registers decide)
+  if (t.fill64) kern = t.unroll == 8 ? gather_kernel<true, 8> : gather_kernel<true, 4>;
+  else kern = t.unroll == 8 ? gather_kernel<false, 8> : gather_kernel<false, 4>;
+  // persistent CTAs: as many as are resident at once (registers decide), unless capped
   int per_sm = 4;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kGatherThreads, 0) != cudaSuccess || per_sm < 1) {
     cudaGetLastError();
     per_sm = 4;
   }
+  if (t.ctas_per_sm > 0 && t.ctas_per_sm < per_sm) per_sm = t.ctas_per_sm;
   long long ctas = (items + kGatherThreads / 32 - 1) / (kGatherThreads / 32);
   if (ctas > 148ll * per_sm) ctas = 148ll * per_sm;
-  kern<<<(unsigned)ctas, kGatherThreads, 0, st>>>(g, a, nloops, nsig);
+  kern<<<(unsigned)ctas, kGatherThreads, 0, st>>>(g, a, row_begin, nrows, grp, (unsigned)items);
   SFFTB_LAUNCH_CHECK();
+  return 0;
+}
+
+int launch_gather(const LoopGeom &g, const GatherArgs &a, int nloops, int nsig, cudaStream_t st)
+{
+  if (nloops <= 0) return 0;
+  const GatherTune t = gather_tune(g, nloops, nsig);
+  if (!t.persist) {
+    const int maxlog = g.logB[0] > g.logB[1] ? g.logB[0] : g.logB[1];
+    dim3 grid((unsigned)ceil_div(1ll << maxlog, kGatherThreads), (unsigned)nloops, (unsigned)nsig);
+    if (t.fill64) {
+      if (t.unroll == 8) gather_grid_kernel<true, 8><<<grid, kGatherThreads, 0, st>>>(g, a);
+      else gather_grid_kernel<true, 4><<<grid, kGatherThreads, 0, st>>>(g, a);
+    } else {
+      if (t.unroll == 8) gather_grid_kernel<false, 8><<<grid, kGatherThreads, 0, st>>>(g, a);
+      else gather_grid_kernel<false, 4><<<grid, kGatherThreads, 0, st>>>(g, a);
+    }
+    SFFTB_LAUNCH_CHECK();
+    return 0;
+  }
+  const int lb = a.loop_begin, le = a.loop_begin + nloops;
+  if (g.logB[0] == g.logB[1]) return launch_gather_rows(g, a, t, lb, nloops, nsig, st);
+  const int loc_e = le < g.loops_loc ? le : g.loops_loc;
+  if (lb < loc_e && launch_gather_rows(g, a, t, lb, loc_e - lb, nsig, st)) return -1;
+  const int est_b = lb > g.loops_loc ? lb : g.loops_loc;
+  if (est_b < le && launch_gather_rows(g, a, t, est_b, le - est_b, nsig, st)) return -1;
   return 0;
 }
 
@@ -571,58 +653,105 @@ int launch_select(const SelectArgs &a, int nrows, int nsig, cudaStream_t st)
 // which removes duplicates without any table.  v2 adds one more bit test:
 // loc mod W_Comb must be a Comb-approved residue.
 // ---------------------------------------------------------------------------
-__device__ __forceinline__ bool voted_by(const LoopGeom &g, const VoteArgs &a, int s, int j,
-                                         unsigned loc)
+// One CTA per selected bucket (signal s, loop j, entry Ji of J_j): its threads walk the n/B
+// permuted positions of that bucket (cf12.cc:102-115).  The B-bit maps of all location loops
+// sit in shared memory (loops_loc * B/8 bytes: 16 KiB at n = 2^27), the per-loop multipliers in
+// registers, and nothing in the loop divides: 64-bit divisions to recover (loop, entry) from
+// a flat index were most of the old kernel's instructions.
+constexpr int kVoteThreads = 256;
+constexpr int kVoteMaxLoops = 8;        // location loops kept in registers; more -> generic path
+
+template <bool SMEM_MAPS>
+__global__ void __launch_bounds__(kVoteThreads)
+vote_kernel(LoopGeom g, VoteArgs a, int first_loops)
 {
+  extern __shared__ unsigned vote_bm[];          // [loops_loc][words] when SMEM_MAPS
+  const int s = blockIdx.y;
   const int logB = g.logB[0];
   const int logseg = g.logn - logB;
-  const unsigned ai = (unsigned)a.perm[(long long)s * perm_stride(g.loops) + g.loops + j];
-  const unsigned p = (unsigned)(((unsigned long long)ai * loc) & (unsigned)g.n_mask);
-  const unsigned half = (1u << logseg) >> 1;
-  const unsigned Jb = (((p + half) & (unsigned)g.n_mask) >> logseg) & ((1u << logB) - 1u);
+  const unsigned seg = 1u << logseg, half = seg >> 1;
+  const unsigned mask = (unsigned)g.n_mask, Bm = (1u << logB) - 1u;
   const int words = logB >= 5 ? (1 << (logB - 5)) : 1;
-  const unsigned *bm = a.bitmap + (long long)s * a.bm_sig_stride + (long long)j * words;
-  return (__ldg(&bm[Jb >> 5]) >> (Jb & 31)) & 1u;
+  const int L = g.loops_loc;
+  const unsigned *gbm = a.bitmap + (long long)s * a.bm_sig_stride;
+  if (SMEM_MAPS) {
+    for (int i = threadIdx.x; i < L * words; i += kVoteThreads) vote_bm[i] = gbm[i];
+    __syncthreads();
+  }
+  const unsigned *bm = SMEM_MAPS ? vote_bm : gbm;
+  unsigned ai[kVoteMaxLoops];
+#pragma unroll
+  for (int q = 0; q < kVoteMaxLoops; q++)
+    ai[q] = q < L ? (unsigned)a.perm[(long long)s * perm_stride(g.loops) + g.loops + q] : 0u;
+  const unsigned *cb = a.comb_bitmap ? a.comb_bitmap + (long long)s * a.comb_sig_stride : nullptr;
+
+  // a CTA may own several (loop, entry) pairs when the grid was capped
+  for (int e = blockIdx.x; e < first_loops * a.num; e += gridDim.x) {
+    const int j = e / a.num, Ji = e - j * a.num;
+    const unsigned Jv = (unsigned)a.J[(long long)s * a.J_sig_stride + (long long)j * a.num + Ji];
+    // cf12.cc:102: low = ceil((J - 0.5) * n/B) mod n  == J*seg - seg/2 (exact for seg >= 2)
+    const unsigned low = ((Jv << logseg) - half) & mask;
+    const unsigned aj = (unsigned)a.perm[(long long)s * perm_stride(g.loops) + j];
+    for (unsigned t = threadIdx.x; t < seg; t += kVoteThreads) {
+      const unsigned p = (low + t) & mask;
+      const unsigned loc = (aj * p) & mask;                       // n is a power of two <= 2^31
+      const unsigned rres = loc & (unsigned)a.W_mask;              // v2: loc mod W_Comb must be approved
+      if (cb && !((__ldg(&cb[rres >> 5]) >> (rres & 31u)) & 1u)) continue;
+      // emitted by the first loop that votes for it; score = votes over all location loops
+      bool earlier = false;
+      int score = 1;
+#pragma unroll
+      for (int q = 0; q < kVoteMaxLoops; q++) {
+        if (q < L && q != j) {
+          const unsigned Jb = ((((ai[q] * loc) & mask) + half) >> logseg) & Bm;
+          const bool v = (bm[q * words + (Jb >> 5)] >> (Jb & 31u)) & 1u;
+          if (q < j) earlier |= v;
+          else score += v ? 1 : 0;
+        }
+      }
+      if (!earlier && score >= a.thresh) {
+        const int pos = atomicAdd(&a.count[s], 1);
+        if (pos < a.hits_cap) a.hits[(long long)s * a.hits_cap + pos] = (int)loc;
+      }
+    }
+  }
 }
 
-__global__ void __launch_bounds__(256)
-vote_kernel(LoopGeom g, VoteArgs a, long long total_per_sig)
+// more than kVoteMaxLoops location loops (no table of the reference has that many)
+__global__ void __launch_bounds__(kVoteThreads)
+vote_generic_kernel(LoopGeom g, VoteArgs a, int first_loops)
 {
   const int s = blockIdx.y;
   const int logB = g.logB[0];
   const int logseg = g.logn - logB;
-  const unsigned seg = 1u << logseg;
-  const unsigned mask = (unsigned)g.n_mask;
-  const long long per_loop = (long long)a.num << logseg;
-  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < total_per_sig;
-       q += (long long)gridDim.x * blockDim.x) {
-    const int j = (int)(q / per_loop);
-    const long long r = q - (long long)j * per_loop;
-    const int Ji = (int)(r >> logseg);
-    const unsigned t = (unsigned)(r & (seg - 1));
+  const unsigned seg = 1u << logseg, half = seg >> 1;
+  const unsigned mask = (unsigned)g.n_mask, Bm = (1u << logB) - 1u;
+  const int words = logB >= 5 ? (1 << (logB - 5)) : 1;
+  const unsigned *bm = a.bitmap + (long long)s * a.bm_sig_stride;
+  const int *perm = a.perm + (long long)s * perm_stride(g.loops);
+  const unsigned *cb = a.comb_bitmap ? a.comb_bitmap + (long long)s * a.comb_sig_stride : nullptr;
+  for (int e = blockIdx.x; e < first_loops * a.num; e += gridDim.x) {
+    const int j = e / a.num, Ji = e - j * a.num;
     const unsigned Jv = (unsigned)a.J[(long long)s * a.J_sig_stride + (long long)j * a.num + Ji];
-    // cf12.cc:102: low = ceil((J - 0.5) * n/B) mod n  == J*seg - seg/2 (exact for seg >= 2)
-    const unsigned low = ((Jv << logseg) - (seg >> 1)) & mask;
-    const unsigned p = (low + t) & mask;
-    const unsigned aj = (unsigned)a.perm[(long long)s * perm_stride(g.loops) + j];
-    const unsigned loc = (unsigned)(((unsigned long long)aj * p) & mask);
-    if (a.comb_bitmap) {
+    const unsigned low = ((Jv << logseg) - half) & mask;
+    const unsigned aj = (unsigned)perm[j];
+    for (unsigned t = threadIdx.x; t < seg; t += kVoteThreads) {
+      const unsigned loc = (aj * ((low + t) & mask)) & mask;
       const unsigned rres = loc & (unsigned)a.W_mask;
-      const unsigned *cb = a.comb_bitmap + (long long)s * a.comb_sig_stride;
-      if (!((__ldg(&cb[rres >> 5]) >> (rres & 31)) & 1u)) continue;
-    }
-    bool earlier = false;
-    for (int jj = 0; jj < j; jj++)
-      if (voted_by(g, a, s, jj, loc)) { earlier = true; break; }
-    if (earlier) continue;
-    int score = 1;
-    for (int jj = j + 1; jj < g.loops_loc; jj++) {
-      if (score + (g.loops_loc - jj) < a.thresh) break;      // cannot reach the threshold any more
-      score += voted_by(g, a, s, jj, loc) ? 1 : 0;
-    }
-    if (score >= a.thresh) {
-      const int pos = atomicAdd(&a.count[s], 1);
-      if (pos < a.hits_cap) a.hits[(long long)s * a.hits_cap + pos] = (int)loc;
+      if (cb && !((__ldg(&cb[rres >> 5]) >> (rres & 31u)) & 1u)) continue;
+      bool earlier = false;
+      int score = 1;
+      for (int q = 0; q < g.loops_loc; q++) {
+        if (q == j) continue;
+        const unsigned Jb = (((((unsigned)perm[g.loops + q] * loc) & mask) + half) >> logseg) & Bm;
+        const bool v = (__ldg(&bm[q * words + (Jb >> 5)]) >> (Jb & 31u)) & 1u;
+        if (q < j) earlier |= v;
+        else score += v ? 1 : 0;
+      }
+      if (!earlier && score >= a.thresh) {
+        const int pos = atomicAdd(&a.count[s], 1);
+        if (pos < a.hits_cap) a.hits[(long long)s * a.hits_cap + pos] = (int)loc;
+      }
     }
   }
 }
@@ -631,13 +760,19 @@ int launch_vote(const LoopGeom &g, const VoteArgs &a, int nsig, cudaStream_t st)
 {
   const int first_loops = g.loops_loc - a.thresh + 1;
   if (first_loops <= 0) return 0;
-  const int logseg = g.logn - g.logB[0];
-  const long long total = (long long)first_loops * ((long long)a.num << logseg);
-  long long blocks = (total + 255) / 256;
-  const long long cap = 148ll * 32;
+  const int words = g.logB[0] >= 5 ? (1 << (g.logB[0] - 5)) : 1;
+  long long blocks = (long long)first_loops * a.num;
+  const long long share = 148ll * 64 / (nsig < 64 ? nsig : 64);
+  const long long cap = share > 148 ? share : 148;
   if (blocks > cap) blocks = cap;
   dim3 grid((unsigned)blocks, (unsigned)nsig);
-  vote_kernel<<<grid, 256, 0, st>>>(g, a, total);
+  if (g.loops_loc > kVoteMaxLoops) {
+    vote_generic_kernel<<<grid, kVoteThreads, 0, st>>>(g, a, first_loops);
+  } else {
+    const size_t smem = sizeof(unsigned) * (size_t)g.loops_loc * words;
+    if (smem <= 48 * 1024) vote_kernel<true><<<grid, kVoteThreads, smem, st>>>(g, a, first_loops);
+    else vote_kernel<false><<<grid, kVoteThreads, 0, st>>>(g, a, first_loops);
+  }
   SFFTB_LAUNCH_CHECK();
   return 0;
 }
@@ -919,7 +1054,10 @@ int launch_estimate(const LoopGeom &g, const EstimateArgs &a, int nsig, long lon
 // ---------------------------------------------------------------------------
 // v2 structured estimation (see v12_kernels.cuh)
 // ---------------------------------------------------------------------------
-constexpr int kV2LogTile = 9;         // hits per tile = threads per CTA (one CTA per SM; 8 KB runs)
+#ifndef SFFTB_V2_LOG_TILE
+#define SFFTB_V2_LOG_TILE 9
+#endif
+constexpr int kV2LogTile = SFFTB_V2_LOG_TILE;   // hits per tile = threads per CTA (512: one CTA per SM, 8 KB runs)
 constexpr int kV2MaxSmem = 227 * 1024 - 8192;   // dynamic shared memory a CTA may ask for (static: parameters)
 
 __device__ __forceinline__ void v2_slice(const V2StructArgs &a, long long total, long long &lo, long long &hi)
@@ -946,6 +1084,8 @@ v2_regroup_kernel(LoopGeom g, const cplx *__restrict__ xs, cplx *__restrict__ xt
   const int logB = j >= g.loops_loc ? g.logB[1] : g.logB[0];
   const int t = logB - logT;
   if (blockIdx.x == 0 && j == 0 && threadIdx.x == 0) tile_counter[blockIdx.z] = 0u;
+  // per-SM arrival counters of the estimation kernel's start-up skew (behind the tile counters)
+  if (blockIdx.x == 0 && j == 0 && blockIdx.z == 0 && threadIdx.x < 256) tile_counter[gridDim.z + threadIdx.x] = 0u;
   const unsigned o = blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= (1u << logB)) return;
   const unsigned b = (o >> logT) | ((o & ((1u << logT) - 1u)) << t);
@@ -1038,18 +1178,14 @@ __device__ __forceinline__ void mbar_arrive(unsigned bar)
 // the next tile's parameters and issue its copies; everybody else goes straight from the
 // divisions to the medians, so the copies fly under the medians and warps of one CTA
 // drift apart by up to a phase -- FP64-heavy divisions and ALU-heavy medians overlap.
-// INTERLEAVE: the divisions of the imaginary parts are folded into the median network of the
-// real parts (MedianNet::run_with), so FP64-pipe work and ALU-pipe selects of ONE warp
-// overlap instead of alternating in phases; the per-tile parameters are double-buffered
-// because they are then still read after the stage has been released for the next copies.
-template <int L, bool INTERLEAVE>
+template <int L>
 __global__ void __launch_bounds__(1 << kV2LogTile, 512 >> kV2LogTile)
 v2_fused_kernel(LoopGeom g, V2StructArgs a)
 {
   constexpr int logT = kV2LogTile, T = 1 << logT;
   constexpr unsigned kRunBytes = T * sizeof(cplx);
   extern __shared__ __align__(128) cplx v2_stage[];              // [L][T], then the run flags
-  __shared__ V2TileParams prm2[INTERLEAVE ? 2 : 1];
+  __shared__ V2TileParams prm;
   __shared__ __align__(8) unsigned long long bars[2];            // full, empty
   const int sig = blockIdx.y;
   const int logNW = g.logn - a.logW;
@@ -1075,7 +1211,17 @@ v2_fused_kernel(LoopGeom g, V2StructArgs a)
     mbar_init(full, L);
     mbar_init(empty, T / 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    prm2[0].chunk = atomicAdd(ctr, 1u);
+    if (a.skew_cycles > 0) {
+      // two CTAs share an SM (T = 256): the second to arrive starts half a tile period late, so
+      // that one CTA's FP64-heavy divisions run under the other's ALU-heavy medians
+      unsigned smid;
+      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+      if (atomicAdd(a.tile_counter + gridDim.y + (smid & 255u), 1u) & 1u) {
+        const long long t0 = clock64();
+        while (clock64() - t0 < a.skew_cycles) {}
+      }
+    }
+    prm.chunk = atomicAdd(ctr, 1u);
   }
   __syncthreads();
 
@@ -1093,14 +1239,11 @@ v2_fused_kernel(LoopGeom g, V2StructArgs a)
   int p_i = -1;
   unsigned p_bucket = 0;
   bool p_fbad = false;
-  long long p_tile = lo + (long long)prm2[0].chunk * kV2Chunk;      // next tile to issue
+  long long p_tile = lo + (long long)prm.chunk * kV2Chunk;      // next tile to issue
   long long p_chunk_end = p_tile + kV2Chunk;
   unsigned p_pending = 0;
-  int p_buf = 0;                                                 // parameter buffer of the next tile
   // writes the parameters of tile `p_tile` (or the end marker) and releases `full`
   auto issue_tile = [&]() {
-    V2TileParams &prm = prm2[p_buf];
-    if (INTERLEAVE) p_buf ^= 1;
     if (p_tile >= hi) {
       if (pj == 0) prm.tile = -1;
       mbar_arrive(full);
@@ -1154,7 +1297,6 @@ v2_fused_kernel(LoopGeom g, V2StructArgs a)
   unsigned parity = 0;
   while (true) {
     mbar_wait(full, parity);
-    const V2TileParams &prm = prm2[INTERLEAVE ? parity : 0];
     const long long tile = prm.tile;
     if (tile < 0) break;
     const unsigned r = prm.r;
@@ -1169,8 +1311,7 @@ v2_fused_kernel(LoopGeom g, V2StructArgs a)
       const double ac = __dmul_rn(sv.x, f.x), bd = __dmul_rn(sv.y, f.y);
       const double ad = __dmul_rn(sv.x, f.y), bc = __dmul_rn(sv.y, f.x);
       vr[j] = div_fast(__dadd_rn(ac, bd), dr.x, dr.y);                             // :388-398
-      // INTERLEAVE: only the numerator now, the division rides inside the first median
-      vi[j] = INTERLEAVE ? __dsub_rn(ad, bc) : div_fast(__dsub_rn(ad, bc), dr.x, dr.y);
+      vi[j] = div_fast(__dsub_rn(ad, bc), dr.x, dr.y);
     }
     if (unsafe) {
       // some input of this tile is zero or outside the band where div_fast is proven
@@ -1199,19 +1340,7 @@ v2_fused_kernel(LoopGeom g, V2StructArgs a)
     }
     parity ^= 1u;
 
-    double re;
-    if (INTERLEAVE) {
-      // the parameters of this tile stay valid (double-buffered) although the stage is released
-      re = MedianNet<L>::run_with(vr, [&](auto step) {
-        constexpr int j = decltype(step)::value;
-        if (j < L && !unsafe) {
-          const double2 dr = prm.dr[j];
-          vi[j] = div_fast(vi[j], dr.x, dr.y);
-        }
-      });
-    } else {
-      re = MedianNet<L>::run(vr);
-    }
+    const double re = MedianNet<L>::run(vr);
     const double im = MedianNet<L>::run(vi);
     const unsigned c = (unsigned)(tile & ((1ll << sbits) - 1));
     const unsigned jj = c + (u << sbits);
@@ -1246,6 +1375,13 @@ int launch_v2_struct(const LoopGeom &g, const V2StructArgs &a, int max_comb, int
   constexpr int logT = kV2LogTile, T = 1 << logT;
   const int maxlog = g.logB[0] > g.logB[1] ? g.logB[0] : g.logB[1];
   dim3 rgrid(1u << (maxlog - logT), (unsigned)g.loops, (unsigned)nsig);
+  V2StructArgs aa = a;
+  static int skew = -1;
+  if (skew < 0) {
+    const char *e = getenv("SFFTB_V2_SKEW");
+    skew = e ? atoi(e) : 0;
+  }
+  aa.skew_cycles = (512 >> kV2LogTile) > 1 ? skew : 0;
   v2_regroup_kernel<<<rgrid, T, 0, st>>>(g, a.xs, a.xt, a.run_unsafe, a.tile_counter);
   SFFTB_LAUNCH_CHECK();
   const size_t flag_bytes = ((size_t)(g.x_samp_size >> logT) + 15) & ~(size_t)15;
@@ -1256,22 +1392,12 @@ int launch_v2_struct(const LoopGeom &g, const V2StructArgs &a, int max_comb, int
   if (ctas < 1) ctas = 1;
   if (ctas > chunks) ctas = chunks;
   dim3 grid((unsigned)ctas, (unsigned)nsig);
-  static int interleave = -1;
-  if (interleave < 0) {
-    const char *e = getenv("SFFTB_V2_INTERLEAVE");
-    interleave = e ? atoi(e) : 0;
-  }
   switch (g.loops) {
 #define SFFTB_V2F_CASE(N)                                                                         \
   case N: {                                                                                       \
-    SFFTB_ONCE_PER_DEVICE({                                                                       \
-      SFFTB_CUDA(cudaFuncSetAttribute(v2_fused_kernel<N, false>,                                  \
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kV2MaxSmem));  \
-      SFFTB_CUDA(cudaFuncSetAttribute(v2_fused_kernel<N, true>,                                   \
-                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kV2MaxSmem));  \
-    });                                                                                           \
-    if (interleave) v2_fused_kernel<N, true><<<grid, T, smem, st>>>(g, a);                        \
-    else v2_fused_kernel<N, false><<<grid, T, smem, st>>>(g, a);                                  \
+    SFFTB_ONCE_PER_DEVICE(SFFTB_CUDA(cudaFuncSetAttribute(                                        \
+        v2_fused_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, kV2MaxSmem)));           \
+    v2_fused_kernel<N><<<grid, T, smem, st>>>(g, aa);                                             \
   } break;
     SFFTB_V2F_CASE(2) SFFTB_V2F_CASE(3) SFFTB_V2F_CASE(4) SFFTB_V2F_CASE(5) SFFTB_V2F_CASE(6)
     SFFTB_V2F_CASE(7) SFFTB_V2F_CASE(8) SFFTB_V2F_CASE(9) SFFTB_V2F_CASE(10) SFFTB_V2F_CASE(11)

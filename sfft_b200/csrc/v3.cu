@@ -57,6 +57,9 @@ struct PlanV3 {
   int *d_rounds = nullptr;         // [cap]
   int *d_draw = nullptr;           // [cap][8]
   long long *d_prof = nullptr;     // [cap][8] cycle counters of the peeling phases
+  int *d_aux = nullptr;            // [cap][aux_ints] team scratch (v3_peel_kernel)
+  int flag_words = 0, aux_ints = 0;
+  int team = 1;                    // CTAs per signal in the peeling kernel (a thread-block cluster)
   int *h_draw[kStageSlots] = {nullptr};
   cudaEvent_t ev[kStageSlots] = {nullptr};
   int next_slot = 0;
@@ -71,6 +74,8 @@ struct V3Geom {
   int fw_half1, fw_half2;
   long long nslots;
   int est_cap, ans_cap, tgt_cap, hash_size, log_hash;
+  int flag_words;          // ceil(max bucket count / 32)
+  int aux_ints;            // per-signal ints of the team's scratch: est_cap + flag_words + exchange + counters
 };
 
 // draw layout per signal: a, ai, b, shift, init_offset, init_G_offset
@@ -180,6 +185,7 @@ struct PeelArgs {
   int *ans_key; cplx *ans_val;
   int *count, *rounds;
   const cplx *fwin1, *fwin2;
+  int *aux;             // [cap][aux_ints] team scratch
   long long *prof;      // per-signal cycle counters of the peeling phases (8 slots)
 };
 
@@ -193,6 +199,8 @@ struct PeelCtx {
   int *hkey, *hidx;
   int *ans_key; cplx *ans_val;
   const cplx *fwin1, *fwin2;
+  int *scr;             // [est_cap] per-item scratch of ans_accumulate
+  unsigned *flagw;      // [flag_words] decode flags
 };
 
 __device__ __forceinline__ cplx fwin_at(const cplx *__restrict__ fwin, int half, int n, int dist)
@@ -341,57 +349,105 @@ __device__ __forceinline__ bool decode_one_gauss(const PeelCtx &c, int which, in
   return true;
 }
 
+// ---- the team: the threads that peel ONE signal --------------------------------------
+// One CTA for small plans; a thread-block cluster of up to 16 CTAs (16 SMs) for large ones.
+// Everything the peeling loop does is either independent per bucket / per found coefficient
+// (decode: two atan2, a sincos and a sqrt in double precision per occupied bucket; targets:
+// six sincos per coefficient) or an ordered compaction, so it spreads over the team with one
+// hardware cluster barrier where the single-CTA version had a __syncthreads(); one SM has
+// 64 FP64 lanes, a 16-CTA team has 1024.  State shared by the team lives in global memory
+// (L2); barrier.cluster's release/acquire at cluster scope orders it (and drops stale L1 lines).
+constexpr int kMaxTeam = 16;
+struct Team {
+  int rank, size;          // this CTA's rank in the team, CTAs in the team
+  int tid, nthreads;       // thread index in the team, threads in the team
+  int *xch;                // [4][kMaxTeam][4] exchange slots (global)
+  int *ctr;                // [4] global counters: 0 touched buckets, 1 segment allocator
+  int seq;                 // exchanges done so far (uniform over the team)
+  __device__ __forceinline__ void sync() const
+  {
+    if (size == 1) { __syncthreads(); return; }
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+  }
+  // every CTA contributes up to three ints; returns, per component, the sum over the CTAs
+  // before this one (`before`) and over all (`total`).  One team barrier.
+  __device__ void exchange3(int v0, int v1, int v2, int *before, int *total)
+  {
+    int *slot = xch + (seq & 3) * kMaxTeam * 4;
+    seq++;
+    if (threadIdx.x == 0) { slot[rank * 4 + 0] = v0; slot[rank * 4 + 1] = v1; slot[rank * 4 + 2] = v2; }
+    sync();
+    int b[3] = {0, 0, 0}, t[3] = {0, 0, 0};
+    for (int q = 0; q < size; q++)
+      for (int e = 0; e < 3; e++) {
+        const int v = slot[q * 4 + e];
+        if (q < rank) b[e] += v;
+        t[e] += v;
+      }
+    for (int e = 0; e < 3; e++) { before[e] = b[e]; total[e] = t[e]; }
+  }
+};
+
 // Decode every bucket of one filter (which: 0 aliasing, 1 first window, 2 permuted window)
 // and list what was found in ascending bucket order, as the reference's loops do.
-// Phase 1: all buckets in parallel; a found (key, value) is parked at its bucket index and
-// flagged in a shared bit map.  Phase 2: one block scan over the flag words places the
-// entries.  Two barriers per 64 Ki buckets instead of two per 1024.
-constexpr int kFlagWords = 2048;
-__device__ int decode_filter(const PeelCtx &c, int which, unsigned *warp_tot, unsigned *sflags)
+// Pass 1: all buckets in parallel over the team; a found (key, value) is parked at its bucket
+// index and flagged in a bit map (global).  One exchange of per-CTA counts.  Pass 2: every CTA
+// places the entries of its own bucket range behind those of the CTAs before it.
+constexpr int kDecodeAhead = 4;     // loads of several chunks in flight
+__device__ int decode_filter(const PeelCtx &c, Team &tm, int which, unsigned *warp_tot)
 {
   const V3Geom &g = c.g;
   const int nb = which == 0 ? g.W : (which == 1 ? g.B1 : g.B2);
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31;
   int *park_key = c.t_slot;          // free between peel steps
   cplx *park_val = c.t_delta;
-  int found = 0;
-  for (int sbase = 0; sbase < nb; sbase += kFlagWords * 32) {
-    const int span = nb - sbase < kFlagWords * 32 ? nb - sbase : kFlagWords * 32;
-    const cplx *p0 = c.samp + (which == 0 ? man_base(g) : (which == 1 ? g1_base(g) : g2_base(g)));
-    const cplx *p1 = p0 + nb;
-    constexpr int kAhead = 4;          // loads of several chunks in flight: one CTA has little else to hide latency
-    for (int cb0 = 0; cb0 < span; cb0 += kAhead * kPeelThreads) {
-      cplx s0[kAhead], s1[kAhead];
+  unsigned *flagw = c.flagw;
+  // contiguous bucket range of this CTA, a whole number of flag words; a filter of at most
+  // 2048 buckets is CTA 0's alone (its placement then needs no counts from anybody else)
+  const int nwords = (nb + 31) >> 5;
+  const bool solo = nb <= 2 * kPeelThreads;
+  const int wper = solo ? nwords : (nwords + tm.size - 1) / tm.size;
+  const int w_lo = tm.rank * wper < nwords ? tm.rank * wper : nwords;
+  const int w_hi = w_lo + wper < nwords ? w_lo + wper : nwords;
+  const int b_lo = w_lo * 32, b_hi = w_hi * 32 < nb ? w_hi * 32 : nb;
+  const cplx *p0 = c.samp + (which == 0 ? man_base(g) : (which == 1 ? g1_base(g) : g2_base(g)));
+  const cplx *p1 = p0 + nb;
+  int mine = 0;
+  for (int cb0 = b_lo; cb0 < w_hi * 32; cb0 += kDecodeAhead * kPeelThreads) {
+    cplx s0[kDecodeAhead], s1[kDecodeAhead];
 #pragma unroll
-      for (int u = 0; u < kAhead; u++) {
-        const int rel = cb0 + u * kPeelThreads + tid;
-        if (rel < span) { s0[u] = p0[sbase + rel]; s1[u] = p1[sbase + rel]; }
-      }
-#pragma unroll
-      for (int u = 0; u < kAhead; u++) {
-        const int cb = cb0 + u * kPeelThreads;
-        if (cb >= span) break;
-        const int bk = sbase + cb + tid;
-        int key = 0;
-        cplx val = make_double2(0.0, 0.0);
-        bool have = false;
-        if (cb + tid < span)
-          have = which == 0 ? decode_one_mansour(c, bk, s0[u], s1[u], key, val)
-                            : decode_one_gauss(c, which, bk, s0[u], s1[u], key, val);
-        if (have) { park_key[bk] = key; park_val[bk] = val; }
-        const unsigned bal = __ballot_sync(0xffffffffu, have);
-        if (lane == 0) sflags[(cb >> 5) + warp] = bal;
-      }
+    for (int u = 0; u < kDecodeAhead; u++) {
+      const int bk = cb0 + u * kPeelThreads + tid;
+      if (bk < b_hi) { s0[u] = p0[bk]; s1[u] = p1[bk]; }
     }
-    __syncthreads();
-    const int nwords = (span + 31) >> 5;
-    // each thread owns two consecutive flag words
-    const int w0 = 2 * tid;
-    const unsigned f0 = w0 < nwords ? sflags[w0] : 0u, f1 = w0 + 1 < nwords ? sflags[w0 + 1] : 0u;
-    int total;
-    int pos = found + block_scan_excl(__popc(f0) + __popc(f1), total, warp_tot);
+#pragma unroll
+    for (int u = 0; u < kDecodeAhead; u++) {
+      const int bk = cb0 + u * kPeelThreads + tid;
+      if (cb0 + u * kPeelThreads >= w_hi * 32) break;
+      int key = 0;
+      cplx val = make_double2(0.0, 0.0);
+      bool have = false;
+      if (bk < b_hi)
+        have = which == 0 ? decode_one_mansour(c, bk, s0[u], s1[u], key, val)
+                          : decode_one_gauss(c, which, bk, s0[u], s1[u], key, val);
+      if (have) { park_key[bk] = key; park_val[bk] = val; }
+      const unsigned bal = __ballot_sync(0xffffffffu, have);
+      if (lane == 0 && (bk >> 5) < w_hi) flagw[bk >> 5] = bal;
+      mine += have;
+    }
+  }
+  const int cta_found = block_sum(mine, warp_tot);       // (its barriers also publish the flag words inside the CTA)
+  int before[3] = {0, 0, 0}, total[3];
+  if (!solo) tm.exchange3(cta_found, 0, 0, before, total);
+  // pass 2: ordered placement of this CTA's range, a tile of 2048 flag words at a time
+  int pos0 = before[0];
+  for (int wb = w_lo; wb < w_hi; wb += 2 * kPeelThreads) {
+    const int w0 = wb + 2 * tid;
+    const unsigned f0 = w0 < w_hi ? flagw[w0] : 0u, f1 = w0 + 1 < w_hi ? flagw[w0 + 1] : 0u;
+    int tile_total;
+    int pos = pos0 + block_scan_excl(__popc(f0) + __popc(f1), tile_total, warp_tot);
     unsigned bits = f0;
-    int wbase = sbase + w0 * 32;
+    int wbase = w0 * 32;
     for (int rep = 0; rep < 2; rep++) {
       while (bits) {
         const int bk = wbase + __ffs(bits) - 1;
@@ -402,10 +458,11 @@ __device__ int decode_filter(const PeelCtx &c, int which, unsigned *warp_tot, un
       bits = f1;
       wbase += 32;
     }
-    found += total;
-    __syncthreads();
+    pos0 += tile_total;
   }
-  return found < g.est_cap ? found : g.est_cap;
+  if (solo) tm.exchange3(cta_found, 0, 0, before, total);     // publishes the count and the list
+  else tm.sync();
+  return total[0] < g.est_cap ? total[0] : g.est_cap;
 }
 
 // the 6 deltas one coefficient leaves in a windowed filter's buckets (:354-463)
@@ -461,22 +518,80 @@ __device__ void mansour_targets(const PeelCtx &c, int key, cplx value, int *slot
 // Subtract, from every touched bucket, the deltas of items [0, F) in item order.
 // keys/vals: the items (plain frequencies; the permuted filter sees (key*ai + shift) mod n,
 // :465-482, :944); the flags say which filters to peel.
-// Deterministic whatever the thread timing: targets are counting-sorted by bucket (atomics
-// decide only the order INSIDE a segment), then one thread per touched bucket applies its
-// segment in ascending target id, i.e. in item order.
-__device__ void peel_apply(const PeelCtx &c, const int *keys, const cplx *vals, int F, bool do_g2,
-                           bool do_g1, bool do_man, unsigned *warp_tot)
+// Deterministic whatever the thread timing: targets are grouped by bucket (atomics decide
+// only where a bucket's segment sits and the order INSIDE it), then one thread per touched
+// bucket applies its segment in ascending target id, i.e. in item order.  Four team phases.
+constexpr int kSmallTargets = 1024;     // peel_apply: up to this many targets are handled by CTA 0 in shared memory
+struct PeelSmall {
+  int slot[kSmallTargets];
+  cplx delta[kSmallTargets];
+};
+
+// the targets of item i, part 0 (permuted window, 6), 1 (first window, 6) or 2 (aliasing, 2),
+// written at slots[0..) / deltas[0..) of that part; absent parts leave slot -1
+__device__ __forceinline__ void item_targets(const PeelCtx &c, int part, int key, cplx v, bool enabled, int *slots,
+                                             cplx *deltas)
 {
-  __shared__ int ntouched;
   const V3Geom &g = c.g;
-  const int tid = threadIdx.x;
+  const int cnt = part == 2 ? 2 : 6;
+  for (int q = 0; q < cnt; q++) slots[q] = -1;
+  if (!enabled) return;
+  if (part == 0) {
+    const int key2 = (int)(((((unsigned long long)(unsigned)key * (unsigned)c.ai) & (unsigned)(g.n - 1)) +
+                            (unsigned)c.shift) % (unsigned)g.n);
+    const int a_off = (int)((unsigned)c.a * (unsigned)c.goff);
+    gauss_targets(c, 2, key2, v, a_off, slots, deltas);
+  } else if (part == 1) {
+    gauss_targets(c, 1, key, v, c.goff, slots, deltas);
+  } else {
+    mansour_targets(c, key, v, slots, deltas);
+  }
+}
+
+__device__ void peel_apply(const PeelCtx &c, Team &tm, const int *keys, const cplx *vals, int F, bool do_g2,
+                           bool do_g1, bool do_man, PeelSmall &sm)
+{
+  const V3Geom &g = c.g;
+  if (F == 0) return;                             // uniform over the team
+  if (F * 14 <= kSmallTargets) {
+    // few coefficients (every round but the first ones): CTA 0 alone, everything in shared
+    // memory, one thread per (item, filter) for the trigonometry, then one thread per touched
+    // bucket subtracts that bucket's deltas in ascending target id = item order
+    if (tm.rank == 0) {
+      const int u = threadIdx.x;
+      if (u < 3 * F) {
+        const int i = u / 3, part = u - 3 * i;
+        const bool on = part == 0 ? do_g2 : (part == 1 ? do_g1 : do_man);
+        int sl[6];
+        cplx dl[6];
+        item_targets(c, part, keys[i], vals[i], on, sl, dl);
+        const int base = i * 14 + part * 6;
+        const int cntp = part == 2 ? 2 : 6;
+        for (int q = 0; q < cntp; q++) { sm.slot[base + q] = sl[q]; if (sl[q] >= 0) sm.delta[base + q] = dl[q]; }
+      }
+      __syncthreads();
+      const int T = F * 14;
+      if (u < T) {
+        const int slot = sm.slot[u];
+        bool first = slot >= 0;
+        for (int t = 0; first && t < u; t++) first = sm.slot[t] != slot;
+        if (first) {
+          cplx val = c.samp[slot];
+          for (int t = u; t < T; t++)
+            if (sm.slot[t] == slot) val = csub_rn(val, sm.delta[t]);
+          c.samp[slot] = val;
+        }
+      }
+    }
+    tm.sync();
+    return;
+  }
   int *cnt = c.head;                              // [nslots], zero between calls
   int *fill = c.t_next;                           // [nslots] running fill pointers
   int *touched = c.t_next + g.nslots;             // [nslots] buckets with at least one target
   int *seg = c.t_next + 2 * g.nslots;             // [F*14] target ids grouped by bucket
-  if (tid == 0) ntouched = 0;
-  __syncthreads();
-  for (int i = tid; i < F; i += kPeelThreads) {
+  int *ntouched = tm.ctr + 0, *seg_alloc = tm.ctr + 1;   // zero between calls
+  for (int i = tm.tid; i < F; i += tm.nthreads) {
     const int key = keys[i];
     const cplx v = vals[i];
     int slots[14];
@@ -491,35 +606,37 @@ __device__ void peel_apply(const PeelCtx &c, const int *keys, const cplx *vals, 
     }
     if (do_g1) gauss_targets(c, 1, key, v, c.goff, slots + 6, deltas + 6);
     if (do_man) mansour_targets(c, key, v, slots + 12, deltas + 12);
+    // all 14 counters at once (one round trip), then one slot reservation for the buckets
+    // this item touched first
+    int old[14], nfirst = 0;
 #pragma unroll
     for (int q = 0; q < 14; q++) {
       const int t = i * 14 + q;
       c.t_slot[t] = slots[q];
-      if (slots[q] >= 0) {
-        c.t_delta[t] = deltas[q];
-        if (atomicAdd(&cnt[slots[q]], 1) == 0) touched[atomicAdd(&ntouched, 1)] = slots[q];
-      }
+      if (slots[q] >= 0) c.t_delta[t] = deltas[q];
+      old[q] = slots[q] >= 0 ? atomicAdd(&cnt[slots[q]], 1) : 1;
     }
+#pragma unroll
+    for (int q = 0; q < 14; q++) nfirst += old[q] == 0;
+    int tpos = nfirst ? atomicAdd(ntouched, nfirst) : 0;
+#pragma unroll
+    for (int q = 0; q < 14; q++)
+      if (old[q] == 0) touched[tpos++] = slots[q];
   }
-  __syncthreads();
-  const int T = ntouched;
-  // segment starts: scan the counts of the touched buckets, a tile of 1024 at a time
-  int base = 0;
-  for (int j0 = 0; j0 < T; j0 += kPeelThreads) {
-    const int j = j0 + tid;
-    const int sl = j < T ? touched[j] : -1;
-    int total;
-    const int excl = block_scan_excl(sl >= 0 ? cnt[sl] : 0, total, warp_tot);
-    if (sl >= 0) fill[sl] = base + excl;
-    base += total;
+  tm.sync();
+  const int T = __ldcg(ntouched);
+  // a segment per touched bucket; where it sits does not matter
+  for (int j = tm.tid; j < T; j += tm.nthreads) {
+    const int sl = touched[j];
+    fill[sl] = atomicAdd(seg_alloc, cnt[sl]);
   }
-  __syncthreads();
-  for (int t = tid; t < F * 14; t += kPeelThreads) {
+  tm.sync();
+  for (int t = tm.tid; t < F * 14; t += tm.nthreads) {
     const int slot = c.t_slot[t];
     if (slot >= 0) seg[atomicAdd(&fill[slot], 1)] = t;
   }
-  __syncthreads();
-  for (int j = tid; j < T; j += kPeelThreads) {
+  tm.sync();
+  for (int j = tm.tid; j < T; j += tm.nthreads) {
     const int sl = touched[j];
     const int len = cnt[sl];
     const int *ids = seg + (fill[sl] - len);
@@ -537,7 +654,8 @@ __device__ void peel_apply(const PeelCtx &c, const int *keys, const cplx *vals, 
     c.samp[sl] = val;
     cnt[sl] = 0;
   }
-  __syncthreads();
+  if (tm.tid == 0) { *ntouched = 0; *seg_alloc = 0; }
+  tm.sync();
 }
 
 __device__ __forceinline__ unsigned hash_key(int key, int log_hash)
@@ -565,52 +683,93 @@ __device__ void hash_insert(const PeelCtx &c, int key, int idx)
 }
 
 // ans[key] (+)= val for the F decoded items, new keys appended in item order
-// (:850, :909-913, :969-973, :1025-1029)
-__device__ int ans_accumulate(const PeelCtx &c, int F, int ans_count, bool assign, unsigned *warp_tot,
-                              int *scratch_idx)
+// (:850, :909-913, :969-973, :1025-1029).  Every CTA takes a contiguous block of the items:
+// pass 1 looks every key up and ranks the new ones inside the block, one exchange of the
+// per-CTA counts, pass 2 appends / accumulates.  Keys of one decode pass are distinct.
+__device__ int ans_accumulate(const PeelCtx &c, Team &tm, int F, int ans_count, bool assign, unsigned *warp_tot)
 {
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int base = 0; base < F; base += kPeelThreads) {
+  if (F == 0) return ans_count;                     // uniform over the team
+  if (F <= kPeelThreads) {
+    // one item per thread of CTA 0; the others only learn the new count
+    int newc = 0;
+    if (tm.rank == 0) {
+      const int i = threadIdx.x;
+      const bool have = i < F;
+      int idx = -1;
+      if (have) idx = hash_find(c, c.est_key[i]);
+      const bool is_new = have && idx < 0;
+      const int excl = block_scan_excl(is_new ? 1 : 0, newc, warp_tot);      // its barriers separate lookups from inserts
+      if (is_new) {
+        idx = ans_count + excl;
+        if (idx < c.g.ans_cap) {
+          c.ans_key[idx] = c.est_key[i];
+          c.ans_val[idx] = make_double2(0.0, 0.0);
+          hash_insert(c, c.est_key[i], idx);
+        }
+      }
+      if (have && idx >= 0 && idx < c.g.ans_cap) {
+        const cplx v = c.est_val[i];
+        c.ans_val[idx] = assign ? v : cadd_rn(c.ans_val[idx], v);
+      }
+    }
+    int before[3], total[3];
+    tm.exchange3(newc, 0, 0, before, total);
+    ans_count += total[0];
+    return ans_count > c.g.ans_cap ? c.g.ans_cap : ans_count;
+  }
+  const int per = (F + tm.size - 1) / tm.size;
+  const int lo = tm.rank * per < F ? tm.rank * per : F;
+  const int hi = lo + per < F ? lo + per : F;
+  int *found_idx = c.scr;            // [est_cap]: >= 0 index in ans, < 0: -(rank among this CTA's new keys) - 1
+  int newc = 0;
+  for (int base = lo; base < hi; base += kPeelThreads) {
     const int i = base + threadIdx.x;
-    const bool have = i < F;
+    const bool have = i < hi;
     int idx = -1;
     if (have) idx = hash_find(c, c.est_key[i]);
     const bool is_new = have && idx < 0;
-    const unsigned bal = __ballot_sync(0xffffffffu, is_new);
-    if (lane == 0) warp_tot[warp] = __popc(bal);
-    __syncthreads();
-    unsigned off = 0, tot = 0;
-    for (int w = 0; w < kPeelThreads / 32; w++) {
-      const unsigned cc = warp_tot[w];
-      if (w < warp) off += cc;
-      tot += cc;
-    }
-    if (is_new) {
-      idx = ans_count + (int)off + __popc(bal & ((1u << lane) - 1u));
+    int total;
+    const int excl = block_scan_excl(is_new ? 1 : 0, total, warp_tot);
+    if (have) found_idx[i] = is_new ? -(newc + excl) - 1 : idx;
+    newc += total;
+  }
+  int before[3], total[3];
+  tm.exchange3(newc, 0, 0, before, total);
+  for (int i = lo + (int)threadIdx.x; i < hi; i += kPeelThreads) {
+    int idx = found_idx[i];
+    if (idx < 0) {
+      idx = ans_count + before[0] + (-idx - 1);
       if (idx < c.g.ans_cap) {
         c.ans_key[idx] = c.est_key[i];
         c.ans_val[idx] = make_double2(0.0, 0.0);
         hash_insert(c, c.est_key[i], idx);
       }
     }
-    if (have && idx >= 0 && idx < c.g.ans_cap) {
+    if (idx >= 0 && idx < c.g.ans_cap) {
       const cplx v = c.est_val[i];
       c.ans_val[idx] = assign ? v : cadd_rn(c.ans_val[idx], v);
     }
-    (void)scratch_idx;
-    ans_count += (int)tot;
-    if (ans_count > c.g.ans_cap) ans_count = c.g.ans_cap;
-    __syncthreads();
   }
+  ans_count += total[0];
+  if (ans_count > c.g.ans_cap) ans_count = c.g.ans_cap;
+  tm.sync();
   return ans_count;
 }
 
 __global__ void __launch_bounds__(kPeelThreads)
-v3_peel_kernel(V3Geom g, PeelArgs a)
+v3_peel_kernel(V3Geom g, PeelArgs a, int team)
 {
   __shared__ unsigned warp_tot[33];
-  __shared__ unsigned sflags[kFlagWords];
-  const int s = blockIdx.x;
+  __shared__ PeelSmall small;
+  const int s = blockIdx.x / team;
+  Team tm;
+  tm.size = team;
+  tm.rank = blockIdx.x % team;
+  tm.tid = tm.rank * kPeelThreads + threadIdx.x;
+  tm.nthreads = team * kPeelThreads;
+  tm.xch = a.aux + (long long)s * g.aux_ints + g.est_cap + g.flag_words;
+  tm.ctr = tm.xch + 4 * kMaxTeam * 4;
+  tm.seq = 0;
   PeelCtx c;
   c.g = g;
   const int *d = a.draw + s * D_INTS;
@@ -627,83 +786,89 @@ v3_peel_kernel(V3Geom g, PeelArgs a)
   c.ans_key = a.ans_key + (long long)s * g.ans_cap;
   c.ans_val = a.ans_val + (long long)s * g.ans_cap;
   c.fwin1 = a.fwin1; c.fwin2 = a.fwin2;
+  c.scr = a.aux + (long long)s * g.aux_ints;
+  c.flagw = reinterpret_cast<unsigned *>(c.scr + g.est_cap);
 
-  for (long long i = threadIdx.x; i < g.nslots; i += kPeelThreads) c.head[i] = 0;
-  for (int i = threadIdx.x; i < g.hash_size; i += kPeelThreads) c.hkey[i] = -1;
-  __syncthreads();
+  for (long long i = tm.tid; i < g.nslots; i += tm.nthreads) c.head[i] = 0;
+  for (int i = tm.tid; i < g.hash_size; i += tm.nthreads) c.hkey[i] = -1;
+  if (tm.tid < 4) tm.ctr[tm.tid] = 0;
+  tm.sync();
 
   long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   long long tmark = clock64();
 #define PROF(slot) { const long long now_ = clock64(); prof[slot] += now_ - tmark; tmark = now_; }
   int ans_count = 0;
   // ---- aliasing filter: decode, record, clear the decoded buckets (:842-855) ----
-  int F = decode_filter(c, 0, warp_tot, sflags);
+  int F = decode_filter(c, tm, 0, warp_tot);
   PROF(0)
-  ans_count = ans_accumulate(c, F, ans_count, true, warp_tot, nullptr);
-  for (int i = threadIdx.x; i < F; i += kPeelThreads) {
+  ans_count = ans_accumulate(c, tm, F, ans_count, true, warp_tot);
+  for (int i = tm.tid; i < F; i += tm.nthreads) {
     // MAN_SAMP[j + 2*(f % W)] = 0 for j = 0,1: in the interleaved layout that is
     // (bucket f % W, shift 0) and (bucket f % W, shift 1)
     const int h = c.est_key[i] & (g.W - 1);
     c.samp[man_base(g) + h] = make_double2(0.0, 0.0);
     c.samp[man_base(g) + g.W + h] = make_double2(0.0, 0.0);
   }
-  __syncthreads();
+  tm.sync();
   if (F == g.k) {
     // :859-860: the reference returns here BEFORE copying its map to the output
-    if (threadIdx.x == 0) { a.count[s] = 0; a.rounds[s] = 0; }
+    if (tm.tid == 0) { a.count[s] = 0; a.rounds[s] = 0; }
     return;
   }
   // ---- first window: peel what is known, decode, peel from window 1 + aliasing (:881-924) ----
   PROF(2)
-  peel_apply(c, c.ans_key, c.ans_val, ans_count, false, true, false, warp_tot);
+  peel_apply(c, tm, c.ans_key, c.ans_val, ans_count, false, true, false, small);
   PROF(4)
-  F = decode_filter(c, 1, warp_tot, sflags);
+  F = decode_filter(c, tm, 1, warp_tot);
   PROF(1)
-  ans_count = ans_accumulate(c, F, ans_count, false, warp_tot, nullptr);
+  ans_count = ans_accumulate(c, tm, F, ans_count, false, warp_tot);
   PROF(2)
-  peel_apply(c, c.est_key, c.est_val, F, false, true, true, warp_tot);
+  peel_apply(c, tm, c.est_key, c.est_val, F, false, true, true, small);
   PROF(3)
   // ---- permuted window (:940-981) ----
-  peel_apply(c, c.ans_key, c.ans_val, ans_count, true, false, false, warp_tot);
+  peel_apply(c, tm, c.ans_key, c.ans_val, ans_count, true, false, false, small);
   PROF(4)
-  F = decode_filter(c, 2, warp_tot, sflags);
+  F = decode_filter(c, tm, 2, warp_tot);
   PROF(1)
-  ans_count = ans_accumulate(c, F, ans_count, false, warp_tot, nullptr);
+  ans_count = ans_accumulate(c, tm, F, ans_count, false, warp_tot);
   PROF(2)
-  peel_apply(c, c.est_key, c.est_val, F, true, true, true, warp_tot);
+  peel_apply(c, tm, c.est_key, c.est_val, F, true, true, true, small);
   PROF(3)
   // ---- round robin until the occupied-bucket counts repeat (:991-1076) ----
   int prev_m = 0, prev_1 = 0, prev_2 = 0, rounds = 0;
   for (int nana = 0;; nana++) {
-    if (nana % 3 == 0) { F = decode_filter(c, 0, warp_tot, sflags); PROF(0) }
-    else { F = decode_filter(c, nana % 3 == 1 ? 1 : 2, warp_tot, sflags); PROF(1) }
-    ans_count = ans_accumulate(c, F, ans_count, false, warp_tot, nullptr);
+    if (nana % 3 == 0) { F = decode_filter(c, tm, 0, warp_tot); PROF(0) }
+    else { F = decode_filter(c, tm, nana % 3 == 1 ? 1 : 2, warp_tot); PROF(1) }
+    ans_count = ans_accumulate(c, tm, F, ans_count, false, warp_tot);
     PROF(2)
-    peel_apply(c, c.est_key, c.est_val, F, true, true, true, warp_tot);
+    peel_apply(c, tm, c.est_key, c.est_val, F, true, true, true, small);
     PROF(3)
     rounds = nana + 1;
     if (nana % 3 == 2) {
       // the reference indexes its interleaved arrays with a plain j < B (:1047-1057):
       // entry j is (bucket j/2, shift j%2)
       int l1 = 0, l2 = 0, lm = 0;
-      for (int j = threadIdx.x; j < g.B1; j += kPeelThreads)
+      for (int j = tm.tid; j < g.B1; j += tm.nthreads)
         l1 += cabs2_rn(c.samp[g1_base(g) + (j & 1) * g.B1 + (j >> 1)]) > 1e-6;
-      for (int j = threadIdx.x; j < g.B2; j += kPeelThreads)
+      for (int j = tm.tid; j < g.B2; j += tm.nthreads)
         l2 += cabs2_rn(c.samp[g2_base(g) + (j & 1) * g.B2 + (j >> 1)]) > 1e-6;
-#pragma unroll 8
-      for (int j = threadIdx.x; j < g.W; j += kPeelThreads) {
+#pragma unroll 4
+      for (int j = tm.tid; j < g.W; j += tm.nthreads) {
         const cplx v = c.samp[man_base(g) + j];
         const double r = v.x / (double)g.W, m = v.y / (double)g.W;
         lm += __dadd_rn(__dmul_rn(r, r), __dmul_rn(m, m)) > 1e-6;
       }
-      const int c1 = block_sum(l1, warp_tot), c2 = block_sum(l2, warp_tot), cm = block_sum(lm, warp_tot);
+      const int b1 = block_sum(l1, warp_tot), b2 = block_sum(l2, warp_tot), bm = block_sum(lm, warp_tot);
+      int before[3], total[3];
+      tm.exchange3(b1, b2, bm, before, total);
+      const int c1 = total[0], c2 = total[1], cm = total[2];
       PROF(5)
       if (prev_m == cm && prev_1 == c1 && prev_2 == c2) break;
       prev_m = cm; prev_1 = c1; prev_2 = c2;
       if (nana > 3000) break;      // safety net; the reference has none
     }
   }
-  if (threadIdx.x == 0) {
+  if (tm.tid == 0) {
     a.count[s] = ans_count;
     a.rounds[s] = rounds;
     if (a.prof)
@@ -734,6 +899,7 @@ static V3Geom make_geom(const PlanImpl *p)
   g.fw_half1 = v.filt[0].fw_half; g.fw_half2 = v.filt[1].fw_half;
   g.nslots = v.nslots;
   g.est_cap = v.est_cap; g.ans_cap = v.ans_cap; g.tgt_cap = v.tgt_cap; g.hash_size = v.hash_size; g.log_hash = v.log_hash;
+  g.flag_words = v.flag_words; g.aux_ints = v.aux_ints;
   return g;
 }
 
@@ -743,6 +909,7 @@ static void v3_free_scratch(PlanV3 &v)
   cudaFree(v.d_t_slot); cudaFree(v.d_t_next); cudaFree(v.d_t_delta); cudaFree(v.d_hkey);
   cudaFree(v.d_hidx); cudaFree(v.d_ans_key); cudaFree(v.d_ans_val); cudaFree(v.d_count);
   cudaFree(v.d_rounds); cudaFree(v.d_draw); cudaFree(v.d_prof); v.d_prof = nullptr;
+  cudaFree(v.d_aux); v.d_aux = nullptr;
   for (int i = 0; i < kStageSlots; i++) {
     if (v.h_draw[i]) cudaFreeHost(v.h_draw[i]);
     v.h_draw[i] = nullptr;
@@ -776,6 +943,7 @@ static int v3_ensure_capacity(PlanImpl *p, int nsig)
   SFFTB_CUDA(cudaMalloc(&v.d_rounds, sizeof(int) * S));
   SFFTB_CUDA(cudaMalloc(&v.d_draw, sizeof(int) * S * D_INTS));
   SFFTB_CUDA(cudaMalloc(&v.d_prof, sizeof(long long) * S * 8));
+  SFFTB_CUDA(cudaMalloc(&v.d_aux, sizeof(int) * S * v.aux_ints));
   for (int i = 0; i < kStageSlots; i++)
     SFFTB_CUDA(cudaHostAlloc(&v.h_draw[i], sizeof(int) * S * D_INTS, cudaHostAllocDefault));
   v.cap = nsig;
@@ -836,6 +1004,16 @@ int v3_build(PlanImpl *p, int n_req, int k)
   v.hash_size = 1;
   v.log_hash = 0;
   while (v.hash_size < 4 * v.ans_cap) { v.hash_size <<= 1; v.log_hash++; }
+  v.flag_words = (cap + 31) / 32;
+  v.aux_ints = v.est_cap + v.flag_words + 4 * kMaxTeam * 4 + 8;
+  // CTAs per signal in the peeling kernel: one SM per 1024 aliasing buckets, at most a
+  // 16-CTA cluster (non-portable size; 8 if the device will not schedule 16)
+  v.team = 1;
+  while (v.team < kMaxTeam && v.team * 1024 < v.W_Man) v.team <<= 1;
+  if (const char *e = getenv("SFFTB_V3_TEAM")) {
+    const int t = atoi(e);
+    if (t == 1 || t == 2 || t == 4 || t == 8 || t == 16) v.team = t;
+  }
   for (int i = 0; i < kStageSlots; i++) SFFTB_CUDA(cudaEventCreateWithFlags(&v.ev[i], cudaEventDisableTiming));
   return v3_ensure_capacity(p, 1);
 }
@@ -866,6 +1044,48 @@ int v3_draw(const PlanImpl *p, sfftb_draw *d)
   d->v3_init_offset = (int)(unsigned)floor(drand48() * n);
   d->v3_init_G_offset = (int)(unsigned)floor(drand48() * n);
   return 0;
+}
+
+// one team (thread-block cluster of `team` CTAs) per signal
+static int launch_peel(const V3Geom &g, const PeelArgs &a, int &team, int nsig, cudaStream_t st)
+{
+  if (team > 8)
+    SFFTB_ONCE_PER_DEVICE(SFFTB_CUDA(cudaFuncSetAttribute(v3_peel_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1)));
+  for (;;) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3((unsigned)(nsig * team));
+    cfg.blockDim = dim3(kPeelThreads);
+    cfg.dynamicSmemBytes = 0;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)team;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = team > 1 ? 1 : 0;
+    if (team > 1) {
+      int nclusters = 0;
+      if (cudaOccupancyMaxActiveClusters(&nclusters, v3_peel_kernel, &cfg) != cudaSuccess || nclusters < 1) {
+        cudaGetLastError();
+        team >>= 1;            // this device will not co-schedule that many CTAs: halve the team
+        continue;
+      }
+    }
+    const cudaError_t e = cudaLaunchKernelEx(&cfg, v3_peel_kernel, g, a, team);
+    if (e != cudaSuccess && team > 1) {
+      cudaGetLastError();
+      team >>= 1;
+      continue;
+    }
+    if (e != cudaSuccess) {
+      set_error(std::string("v3 peel kernel launch -> ") + cudaGetErrorString(e));
+      return -1;
+    }
+    g_launches++;
+    return 0;
+  }
 }
 
 int v3_exec(PlanImpl *p, const cplx *d_in, long long stride, int nsig, const sfftb_draw *draws)
@@ -916,8 +1136,8 @@ int v3_exec(PlanImpl *p, const cplx *d_in, long long stride, int nsig, const sff
   a.count = v.d_count; a.rounds = v.d_rounds;
   a.fwin1 = v.filt[0].fwin; a.fwin2 = v.filt[1].fwin;
   a.prof = v.d_prof;
-  v3_peel_kernel<<<nsig, kPeelThreads, 0, st>>>(g, a);
-  SFFTB_LAUNCH_CHECK();
+  a.aux = v.d_aux;
+  if (launch_peel(g, a, v.team, nsig, st)) return -1;
   timer_mark(p, "peel");
   p->last_nsig = nsig;
   return 0;

@@ -213,8 +213,8 @@ def sharded_matches_single(plan, st, x, draw):
         ok = cnt == cnt1
         if ok:
             o_s, o_1 = torch.argsort(loc_s), torch.argsort(loc_1)
-            ok = bool(torch.equal(loc_s[o_s], loc_1[o_1])) and \
-                bool(torch.equal(val_s.view(torch.int64)[o_s], val_1.view(torch.int64)[o_1]))
+            bits_s, bits_1 = val_s.view(torch.int64).view(-1, 2), val_1.view(torch.int64).view(-1, 2)
+            ok = bool(torch.equal(loc_s[o_s], loc_1[o_1])) and bool(torch.equal(bits_s[o_s], bits_1[o_1]))
     elif ok:
         ok = bool(torch.equal(loc_s, loc_1[off:off + n_slice])) and \
             bool(torch.equal(val_s.view(torch.int64), val_1[off:off + n_slice].view(torch.int64)))

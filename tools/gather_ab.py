@@ -48,10 +48,12 @@ def main():
             for nm, ms in plan.stage_times().items():
                 acc.setdefault(nm, []).append(ms)
     samples = batch * (info["gather_samples"] - (info["Comb_loops"] * info["W_Comb"] if version == 2 else 0))
+    extra = {k: os.environ[k] for k in ("SFFTB_V2_SKEW", "SFFTB_LIB", "SFFTB_GATHER_UNROLL", "SFFTB_V3_TEAM") if k in os.environ}
     g = sum(acc["gather"]) / len(acc["gather"]) if "gather" in acc else None
     out = {"workload": wl, "fill": os.environ.get("SFFTB_GATHER_FILL", "auto"),
            "l2_fetch": os.environ.get("SFFTB_L2_FETCH", "default"), "gather_ms": g, "samples": samples,
            "gsamples_gathered_per_s": samples / (g * 1e-3) / 1e9 if g else None,
+           "env": extra, "total_ms": sum(sum(v) / len(v) for v in acc.values()),
            "stages_ms": {nm: sum(v) / len(v) for nm, v in acc.items()}}
     print(json.dumps(out))
     plan.close()
