@@ -146,9 +146,14 @@ def cpu_reference_run(workload, nsig, steps, warmup, budget_s=150.0):
     from oracle import ref
 
     version, n, k, snr_db, desc = WORKLOADS[workload]
-    kind = "fast" if ref.available("fast") else "parity"
+    # timing build: reference flags over MKL DFTI when this image's libtorch_cpu.so provides it
+    # (validated against numpy.fft by tests/test_oracle_vs_ref.py), else over the oracle's own FFT
+    kind = "mkl" if ref.available("mkl") and ref.mkl_provider() else ("fast" if ref.available("fast") else "parity")
     if not ref.available(kind):
         return {"unavailable": "oracle/_ref not built (needs the reference sources at build time)"}
+    fft_backend = {"mkl": "MKL DFTI from libtorch_cpu.so (not FFTW: FFTW is not installable here)",
+                   "fast": "the oracle's radix-2/Bluestein FFT shim (FFTW is not installable here)",
+                   "parity": "the oracle's radix-2/Bluestein FFT shim, IEEE flags"}[kind]
     cores = min(nsig, os.cpu_count() or 1)
     L = ref.lib(kind)
     t0 = time.time()
@@ -182,8 +187,7 @@ def cpu_reference_run(workload, nsig, steps, warmup, budget_s=150.0):
         "sample": (f"{len(times)} full sfft_exec{'_many' if nsig > 1 else ''} call(s) of {desc}, "
                    f"{nsig} signal(s), same input bits as the GPU arm; reference sources built -O3 -ffast-math "
                    f"-march=x86-64-v3 (not -march=native: the binary is built on another host) -fopenmp "
-                   f"-DNDEBUG over the oracle's radix-2 FFT shim (FFTW is not installable); "
-                   f"plan build {plan_s:.1f}s excluded"),
+                   f"-DNDEBUG over {fft_backend}; plan build {plan_s:.1f}s excluded"),
         "steps_timed": len(times), "ms_per_step": 1e3 * total / len(times),
         "cpu_model": _cpu_model(),
     }
@@ -314,6 +318,48 @@ def device_signal(torch, n, k, seed, snr_db, dev):
         v = torch.rand(n, generator=gd, device=dev, dtype=torch.float64)
         x = x + std * torch.sqrt(-2 * torch.log(u)) * torch.exp(2j * torch.pi * v)
     return x.contiguous()
+
+
+def pcie_probe(ctx):
+    """What the host link gives N ranks AT THE SAME TIME: every rank copies 256 MiB host->device
+    and 256 MiB device->host concurrently (pinned memory, two streams), 5 times; max over
+    ranks.  This is the ceiling of the legacy host-buffer path (`e2e`), which moves 16 n bytes
+    each way per transform."""
+    torch, dist, dev, world = ctx["torch"], ctx["dist"], ctx["dev"], ctx["world"]
+    nbytes, reps = 256 << 20, 5
+    h_in = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    h_out = torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+    d_in = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    d_out = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    s1, s2 = torch.cuda.Stream(device=dev), torch.cuda.Stream(device=dev)
+
+    def once(both):
+        with torch.cuda.stream(s1):
+            d_in.copy_(h_in, non_blocking=True)
+        if both:
+            with torch.cuda.stream(s2):
+                h_out.copy_(d_out, non_blocking=True)
+
+    out = {}
+    for name, both in (("h2d_only", False), ("duplex", True)):
+        once(both)
+        ctx["barrier"]()
+        t0 = time.perf_counter()
+        for _ in range(reps):
+            once(both)
+        torch.cuda.synchronize()
+        t = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        moved = reps * nbytes * (2 if both else 1)
+        out[name + "_gbs_per_rank"] = moved / float(t.item()) / 1e9
+        out[name + "_gbs_aggregate"] = world * moved / float(t.item()) / 1e9
+        ctx["barrier"]()
+    try:
+        out["cpu_affinity"] = len(os.sched_getaffinity(0))
+    except Exception:
+        pass
+    return out
 
 
 def extra_loop_sharded(ctx, plan, x, what):
@@ -565,6 +611,7 @@ def run_ours(args):
     ctx = dict(torch=torch, dist=dist, dev=dev, rank=rank, world=world, stream=stream, barrier=barrier,
                sfft_mod=sfft_mod, steps=args.steps)
     if not args.no_extras:
+        extras["pcie_probe"] = guarded(pcie_probe, ctx)
         if version in (1, 2) and batch == 1:
             # one signal of THIS workload with its loops sharded over all ranks
             extras["loop_sharded_single_signal"] = guarded(
@@ -630,6 +677,14 @@ def run_ours(args):
             "plan_ms": plan_ms,
         }
         line.update(extras)
+        probe = extras.get("pcie_probe") or {}
+        if "duplex_gbs_aggregate" in probe:
+            # the legacy path moves 16 n bytes in and 16 n bytes out per transform
+            e2e_gbs = e2e_value * 1e9 * 32 / 1e9
+            line["e2e"]["host_link_gbs_used"] = e2e_gbs
+            line["e2e"]["host_link_gbs_measured_ceiling"] = probe["duplex_gbs_aggregate"]
+            line["e2e"]["note"] = ("bytes moved over the host link per second by the e2e run vs what N ranks copying "
+                                   "concurrently (pcie_probe, full duplex) reach on this box")
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_reference_run(args.workload, min(batch, 8), 1, 0, budget_s=90.0)

@@ -18,9 +18,26 @@ def available(kind="parity"):
     return os.path.exists(os.path.join(_HERE, "_ref", f"libsfft_ref_{kind}.so"))
 
 
+def mkl_provider():
+    """The shared object that exports MKL's DFTI in this image: PyTorch's libtorch_cpu.so."""
+    import importlib.util
+    spec = importlib.util.find_spec("torch")
+    if not spec or not spec.origin:
+        return None
+    p = os.path.join(os.path.dirname(spec.origin), "lib", "libtorch_cpu.so")
+    return p if os.path.exists(p) else None
+
+
 def lib(kind="parity"):
+    """kind: "parity" (IEEE flags, oracle FFT), "fast" (reference flags, oracle FFT), "mkl"
+    (reference flags over MKL DFTI -- timing baseline only)."""
     if kind in _cache:
         return _cache[kind]
+    if kind == "mkl":
+        prov = mkl_provider()
+        if not prov:
+            raise OSError("no libtorch_cpu.so to take MKL DFTI from")
+        os.environ["SFFT_REF_MKL_LIB"] = prov
     path = os.path.join(_HERE, "_ref", f"libsfft_ref_{kind}.so")
     L = C.CDLL(path, mode=C.RTLD_LOCAL)
     vp, ci, cd = C.c_void_p, C.c_int, C.c_double

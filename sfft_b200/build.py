@@ -91,7 +91,7 @@ def build_tools():
         subprocess.check_call([HOST_CXX, "-O2", f"-DHARNESS_MODE={mode}", src, "-I", os.path.join(root, "include"),
                                "-L", HERE, "-lsfft", f"-Wl,-rpath,{HERE}", "-Wl,-rpath,$ORIGIN/../sfft_b200",
                                "-o", os.path.join(tools, name)])
-    for mb in ("random_gather", "ld_variants", "bulk_copy"):
+    for mb in ("random_gather", "ld_variants", "bulk_copy", "pipe_overlap"):
         cu = os.path.join(tools, "microbench", mb + ".cu")
         if os.path.exists(cu):
             subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",

@@ -36,9 +36,26 @@ void sfftb_host_chirp(int n, int sign, double *out_re_im);
 double sfftb_host_cabs(double re, double im);
 }
 
+#include <chrono>
+
 namespace sfftb {
 
 namespace {
+
+// SFFTB_PLAN_TIMING=1: wall-clock of the builder's steps on stderr (device drained at each mark)
+struct StepClock {
+  bool on;
+  std::chrono::steady_clock::time_point t0;
+  StepClock() : on(getenv("SFFTB_PLAN_TIMING") != nullptr), t0(std::chrono::steady_clock::now()) {}
+  void mark(const char *what)
+  {
+    if (!on) return;
+    cudaDeviceSynchronize();
+    const auto t1 = std::chrono::steady_clock::now();
+    fprintf(stderr, "[libsfft plan] %-28s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+    t0 = t1;
+  }
+};
 
 constexpr int kT = 256;
 inline int grid_for(long long n)
@@ -434,10 +451,13 @@ int build_filters(int logn, int count, const FilterSpec *specs, DeviceFilter **o
     }
     which_win[f] = found;
   }
+  StepClock clk;
   Twiddles twn;
   if (make_twiddles(logn, &twn, st)) return -1;
+  clk.mark("twiddles");
   for (int q = 0; q < nwin; q++)
     if (build_window(logn, &win[q], twn, st)) return -1;
+  clk.mark("window + its spectrum");
 
   // boxcar chains, one stream per filter
   const int cand_cap = 4096;
@@ -460,6 +480,7 @@ int build_filters(int logn, int count, const FilterSpec *specs, DeviceFilter **o
     peak_candidates_kernel<<<grid_for(n), kT, 0, fs[f]>>>(d_H[f], logn, d_maxq[f], d_cand[f], d_ncand[f], cand_cap);
     SFFTB_LAUNCH_CHECK();
   }
+  clk.mark("boxcar + ramp chains");
   for (int f = 0; f < count; f++) {
     const WindowWork &ww = win[which_win[f]];
     int ncand = 0;
@@ -489,6 +510,7 @@ int build_filters(int logn, int count, const FilterSpec *specs, DeviceFilter **o
     SFFTB_CUDA(cudaStreamSynchronize(fs[f]));
     cudaFree(d_T);
   }
+  clk.mark("normalise, inverse FFT, taps");
   for (int f = 0; f < count; f++) {
     cudaStreamDestroy(fs[f]);
     cudaFree(d_H[f]); cudaFree(d_cand[f]); cudaFree(d_maxq[f]); cudaFree(d_ncand[f]);
@@ -498,6 +520,7 @@ int build_filters(int logn, int count, const FilterSpec *specs, DeviceFilter **o
     cudaFree(win[q].d_G); cudaFree(win[q].d_R);
   }
   free_twiddles(&twn);
+  clk.mark("free");
   return 0;
 }
 

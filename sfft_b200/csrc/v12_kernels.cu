@@ -1,5 +1,6 @@
 // v12_kernels.cu -- sm_100a kernels for sFFT v1/v2 (see v12_kernels.cuh).
 #include <stdlib.h>
+#include <string.h>
 
 #include "v12_kernels.cuh"
 
@@ -25,75 +26,20 @@ __device__ __forceinline__ long long loop_offset(const LoopGeom &g, int j)
 // while the taps stream coalesced and stay in L2 across loops.
 // ---------------------------------------------------------------------------
 constexpr int kGatherThreads = 256;
-constexpr int kGatherUnroll = 4;        // independent sample loads a thread keeps in flight (A/B: r02_gather_ab.md)
 
-// Work item = 32 consecutive buckets of one (loop, signal): one warp.  CTAs are persistent (as
-// many as are resident at once) and warps stride over the items, so every SM gets the same
-// number of items whatever the shape -- a grid of one CTA per 256 buckets left the last wave
-// of C2 (1280 CTAs on 592 slots) running on a sixth of the machine.  One launch covers rows of
-// ONE bucket count (location rows, or estimation rows), so an item number decodes with
-// shifts and one 32-bit division; a warp spends its time waiting for samples, not on that.
+// One CTA per 256 buckets of one (loop, signal), CTAs handed out by the hardware scheduler.
+// U = independent sample loads a thread issues back to back.  Measured (profiles/r02_gather_ab.md):
+// the gather is bound by the random-request rate of the memory system; with every warp slot of
+// the SM occupied, SHORT bursts per thread are faster when the signal lives in HBM -- U = 2
+// beats U = 8 by 17-19 % at C2 and C4 -- while U = 8 wins when it is L2-resident (n <= 2^22:
+// C1, C5).  Capping the resident CTAs, or a persistent statically strided form of the same
+// loop, was slower at every shape; both were dropped.
 // FILL64: ask L2 for 64-byte fills around a sample instead of the whole 128-byte line; the
 // neighbours of a permuted sample are not wanted soon (halves the DRAM traffic, same or
-// better time at every BASELINE shape: profiles/r02_gather_ab.md).
-template <bool FILL64, int kGatherUnroll>
+// better time at every BASELINE shape).
+template <bool FILL64, int U>
 __global__ void __launch_bounds__(kGatherThreads)
-gather_kernel(LoopGeom g, GatherArgs a, int row_begin, int nrows, int grp, unsigned items)
-{
-  const int lane = threadIdx.x & 31;
-  const unsigned warps_per_cta = kGatherThreads / 32;
-  const unsigned mask = (unsigned)g.n_mask;
-  const int logB = g.logB[grp];
-  const int lc = logB > 5 ? logB - 5 : 0;            // log2(items per row)
-  const unsigned B = 1u << logB;
-  const cplx *__restrict__ xbase = a.x_indirect ? reinterpret_cast<const cplx *>(*a.x_indirect) : a.x;
-  for (unsigned it = blockIdx.x * warps_per_cta + (threadIdx.x >> 5); it < items; it += gridDim.x * warps_per_cta) {
-    const unsigned row = it >> lc, chunk = it & ((1u << lc) - 1u);
-    const unsigned s = row / (unsigned)nrows;
-    const int j = row_begin + (int)(row - s * (unsigned)nrows);
-    const unsigned b = chunk * 32u + (unsigned)lane;
-    if (b >= B) continue;
-    const int est = j >= g.loops_loc ? 1 : 0;        // rows of both kinds share a launch when B_loc == B_est
-    const int w = g.w[est];
-    const cplx *__restrict__ taps = a.taps[est];
-    const cplx *__restrict__ x = xbase + (long long)s * a.x_stride;
-    const unsigned ai = (unsigned)a.perm[(long long)s * perm_stride(g.loops) + g.loops + j];
-
-    unsigned idx = (b * ai) & mask;                  // n is a power of two <= 2^31
-    const unsigned stepB = (B * ai) & mask;
-
-    double acc_re = 0.0, acc_im = 0.0;
-    for (unsigned i = b; i < (unsigned)w; i += kGatherUnroll * B) {
-      cplx xv[kGatherUnroll], tv[kGatherUnroll];
-      unsigned id = idx;
-#pragma unroll
-      for (int u = 0; u < kGatherUnroll; u++) {
-        const unsigned ii = i + u * B;
-        xv[u] = FILL64 ? ldg_stream64(x + id) : ldg_stream(x + id);
-        tv[u] = __ldg(taps + (ii < (unsigned)w ? ii : 0u));
-        id = (id + stepB) & mask;
-      }
-      idx = id;
-#pragma unroll
-      for (int u = 0; u < kGatherUnroll; u++) {
-        const unsigned ii = i + u * B;
-        if (ii < (unsigned)w) {
-          const cplx p = cmul_rn(xv[u], tv[u]);
-          acc_re = __dadd_rn(acc_re, p.x);
-          acc_im = __dadd_rn(acc_im, p.y);
-        }
-      }
-    }
-    cplx *xs = a.xs + (long long)s * g.x_samp_size + loop_offset(g, j);
-    xs[bitrev(b, logB)] = make_double2(acc_re, acc_im);
-  }
-}
-
-// The same arithmetic on a plain grid: one CTA per 256 buckets of one (loop, signal), CTAs
-// handed out by the hardware scheduler.  Used where the grid is many waves deep (batches).
-template <bool FILL64, int kGatherUnroll>
-__global__ void __launch_bounds__(kGatherThreads)
-gather_grid_kernel(LoopGeom g, GatherArgs a)
+gather_kernel(LoopGeom g, GatherArgs a)
 {
   const int j = a.loop_begin + blockIdx.y;
   const int s = blockIdx.z;
@@ -108,14 +54,14 @@ gather_grid_kernel(LoopGeom g, GatherArgs a)
       (a.x_indirect ? reinterpret_cast<const cplx *>(*a.x_indirect) : a.x) + (long long)s * a.x_stride;
   const unsigned ai = (unsigned)a.perm[(long long)s * perm_stride(g.loops) + g.loops + j];
   const unsigned mask = (unsigned)g.n_mask;
-  unsigned idx = (b * ai) & mask;
+  unsigned idx = (b * ai) & mask;                    // n is a power of two <= 2^31
   const unsigned stepB = (B * ai) & mask;
   double acc_re = 0.0, acc_im = 0.0;
-  for (unsigned i = b; i < (unsigned)w; i += kGatherUnroll * B) {
-    cplx xv[kGatherUnroll], tv[kGatherUnroll];
+  for (unsigned i = b; i < (unsigned)w; i += U * B) {
+    cplx xv[U], tv[U];
     unsigned id = idx;
 #pragma unroll
-    for (int u = 0; u < kGatherUnroll; u++) {
+    for (int u = 0; u < U; u++) {
       const unsigned ii = i + u * B;
       xv[u] = FILL64 ? ldg_stream64(x + id) : ldg_stream(x + id);
       tv[u] = __ldg(taps + (ii < (unsigned)w ? ii : 0u));
@@ -123,7 +69,7 @@ gather_grid_kernel(LoopGeom g, GatherArgs a)
     }
     idx = id;
 #pragma unroll
-    for (int u = 0; u < kGatherUnroll; u++) {
+    for (int u = 0; u < U; u++) {
       const unsigned ii = i + u * B;
       if (ii < (unsigned)w) {
         const cplx p = cmul_rn(xv[u], tv[u]);
@@ -136,85 +82,34 @@ gather_grid_kernel(LoopGeom g, GatherArgs a)
   xs[bitrev(b, logB)] = make_double2(acc_re, acc_im);
 }
 
-// how a gather is launched; defaults by shape, every field overridable from the environment
-// while tuning (SFFTB_GATHER_MODE=grid|persist, SFFTB_GATHER_UNROLL=4|8, SFFTB_GATHER_CTAS=<per SM>,
-// SFFTB_GATHER_FILL=64|128; read at every launch so one process can sweep them)
-struct GatherTune {
-  bool persist;
-  int unroll;
-  int ctas_per_sm;     // persistent mode: cap on resident CTAs per SM (0: whatever fits)
-  bool fill64;
-};
-static GatherTune gather_tune(const LoopGeom &g, int nloops, int nsig)
-{
-  GatherTune t;
-  // waves of the plain grid: a shallow grid ends on a ragged last wave, which the persistent
-  // form avoids; a deep one (batches) is balanced already
-  const int maxlog = g.logB[0] > g.logB[1] ? g.logB[0] : g.logB[1];
-  const double waves = (double)ceil_div(1ll << maxlog, kGatherThreads) * nloops * nsig / (148.0 * 4);
-  t.persist = g.logB[0] == g.logB[1] && waves > 1.0 && waves < 3.0;
-  t.unroll = t.persist ? 4 : 8;
-  t.ctas_per_sm = 0;
-  t.fill64 = true;
-  if (getenv("SFFTB_TUNE")) {
-    if (const char *e = getenv("SFFTB_GATHER_MODE")) t.persist = e[0] == 'p';
-    if (const char *e = getenv("SFFTB_GATHER_UNROLL")) t.unroll = atoi(e) == 8 ? 8 : 4;
-    if (const char *e = getenv("SFFTB_GATHER_CTAS")) t.ctas_per_sm = atoi(e);
-    if (const char *e = getenv("SFFTB_GATHER_FILL")) t.fill64 = atoi(e) != 128;
-  }
-  return t;
-}
-
-// rows [row_begin, row_begin + nrows) of every signal, all with the same bucket count
-static int launch_gather_rows(const LoopGeom &g, const GatherArgs &a, const GatherTune &t, int row_begin, int nrows,
-                              int nsig, cudaStream_t st)
-{
-  if (nrows <= 0) return 0;
-  const int grp = row_begin >= g.loops_loc ? 1 : 0;
-  const int lc = g.logB[grp] > 5 ? g.logB[grp] - 5 : 0;
-  const long long items = ((long long)nrows * nsig) << lc;
-  if (items >= (1ll << 32)) { set_error("launch_gather: batch too large for one launch"); return -1; }
-  typedef void (*kern_t)(LoopGeom, GatherArgs, int, int, int, unsigned);
-  kern_t kern;
-  if (t.fill64) kern = t.unroll == 8 ? gather_kernel<true, 8> : gather_kernel<true, 4>;
-  else kern = t.unroll == 8 ? gather_kernel<false, 8> : gather_kernel<false, 4>;
-  // persistent CTAs: as many as are resident at once (registers decide), unless capped
-  int per_sm = 4;
-  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, kGatherThreads, 0) != cudaSuccess || per_sm < 1) {
-    cudaGetLastError();
-    per_sm = 4;
-  }
-  if (t.ctas_per_sm > 0 && t.ctas_per_sm < per_sm) per_sm = t.ctas_per_sm;
-  long long ctas = (items + kGatherThreads / 32 - 1) / (kGatherThreads / 32);
-  if (ctas > 148ll * per_sm) ctas = 148ll * per_sm;
-  kern<<<(unsigned)ctas, kGatherThreads, 0, st>>>(g, a, row_begin, nrows, grp, (unsigned)items);
-  SFFTB_LAUNCH_CHECK();
-  return 0;
-}
-
 int launch_gather(const LoopGeom &g, const GatherArgs &a, int nloops, int nsig, cudaStream_t st)
 {
   if (nloops <= 0) return 0;
-  const GatherTune t = gather_tune(g, nloops, nsig);
-  if (!t.persist) {
-    const int maxlog = g.logB[0] > g.logB[1] ? g.logB[0] : g.logB[1];
-    dim3 grid((unsigned)ceil_div(1ll << maxlog, kGatherThreads), (unsigned)nloops, (unsigned)nsig);
-    if (t.fill64) {
-      if (t.unroll == 8) gather_grid_kernel<true, 8><<<grid, kGatherThreads, 0, st>>>(g, a);
-      else gather_grid_kernel<true, 4><<<grid, kGatherThreads, 0, st>>>(g, a);
-    } else {
-      if (t.unroll == 8) gather_grid_kernel<false, 8><<<grid, kGatherThreads, 0, st>>>(g, a);
-      else gather_grid_kernel<false, 4><<<grid, kGatherThreads, 0, st>>>(g, a);
+  const int maxlog = g.logB[0] > g.logB[1] ? g.logB[0] : g.logB[1];
+  dim3 grid((unsigned)ceil_div(1ll << maxlog, kGatherThreads), (unsigned)nloops, (unsigned)nsig);
+  int unroll = g.logn <= 22 ? 8 : 2;
+  bool fill64 = true;
+  size_t pad = 0;                                    // dynamic shared memory nobody uses: caps the CTAs per SM
+  if (getenv("SFFTB_TUNE")) {
+    // read at every launch so that one process can sweep them (tools/gather_sweep.py)
+    if (const char *e = getenv("SFFTB_GATHER_UNROLL")) unroll = atoi(e);
+    if (const char *e = getenv("SFFTB_GATHER_FILL")) fill64 = atoi(e) != 128;
+    if (const char *e = getenv("SFFTB_GATHER_SMEM")) pad = (size_t)atoi(e);
+    if (pad > 48 * 1024) {
+      cudaFuncSetAttribute(gather_kernel<true, 8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(gather_kernel<true, 4>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+      cudaFuncSetAttribute(gather_kernel<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     }
-    SFFTB_LAUNCH_CHECK();
-    return 0;
   }
-  const int lb = a.loop_begin, le = a.loop_begin + nloops;
-  if (g.logB[0] == g.logB[1]) return launch_gather_rows(g, a, t, lb, nloops, nsig, st);
-  const int loc_e = le < g.loops_loc ? le : g.loops_loc;
-  if (lb < loc_e && launch_gather_rows(g, a, t, lb, loc_e - lb, nsig, st)) return -1;
-  const int est_b = lb > g.loops_loc ? lb : g.loops_loc;
-  if (est_b < le && launch_gather_rows(g, a, t, est_b, le - est_b, nsig, st)) return -1;
+  if (fill64) {
+    if (unroll >= 8) gather_kernel<true, 8><<<grid, kGatherThreads, pad, st>>>(g, a);
+    else if (unroll >= 4) gather_kernel<true, 4><<<grid, kGatherThreads, pad, st>>>(g, a);
+    else gather_kernel<true, 2><<<grid, kGatherThreads, pad, st>>>(g, a);
+  } else {
+    if (unroll >= 8) gather_kernel<false, 8><<<grid, kGatherThreads, pad, st>>>(g, a);
+    else gather_kernel<false, 4><<<grid, kGatherThreads, pad, st>>>(g, a);
+  }
+  SFFTB_LAUNCH_CHECK();
   return 0;
 }
 
@@ -614,6 +509,317 @@ static int launch_select_big(const SelectArgs &a, int nrows, int nsig, cudaStrea
   return 0;
 }
 
+// ---------------------------------------------------------------------------
+// Rows of 2^15 .. 2^18 buckets in ONE kernel: a thread-block cluster per row, every CTA
+// keeping 16384 keys of the row in its own shared memory.  The MSD radix select runs as in
+// select_kernel; the only cross-CTA steps go through distributed shared memory -- each pass
+// adds the CTAs' digit histograms into CTA 0's (red.shared::cluster), one cluster barrier,
+// and everybody reads the merged histogram back; once at most kSelectCand keys share the
+// decided prefix they are gathered into CTA 0, which finishes alone and publishes the
+// cutoff; the ordered placement needs the (greater, equal) counts of the lower-ranked CTAs.
+// ~8 cluster barriers instead of a chain of 11 kernels (60 us -> see profiles/r02_*).
+// ---------------------------------------------------------------------------
+constexpr int kClusterKeys = 16384;     // keys per CTA
+constexpr int kMaxSelectCluster = 16;
+
+__device__ __forceinline__ unsigned map_to_rank(const void *smem_ptr, unsigned rank)
+{
+  unsigned local = (unsigned)__cvta_generic_to_shared(smem_ptr), remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(local), "r"(rank));
+  return remote;
+}
+__device__ __forceinline__ void dsmem_red_add(unsigned addr, unsigned v)
+{
+  asm volatile("red.relaxed.cluster.shared::cluster.add.u32 [%0], %1;" ::"r"(addr), "r"(v) : "memory");
+}
+__device__ __forceinline__ unsigned dsmem_atom_add(unsigned addr, unsigned v)
+{
+  unsigned old;
+  asm volatile("atom.relaxed.cluster.shared::cluster.add.u32 %0, [%1], %2;" : "=r"(old) : "r"(addr), "r"(v) : "memory");
+  return old;
+}
+__device__ __forceinline__ unsigned dsmem_ld_u32(unsigned addr)
+{
+  unsigned v;
+  asm volatile("ld.shared::cluster.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ unsigned long long dsmem_ld_u64(unsigned addr)
+{
+  unsigned long long v;
+  asm volatile("ld.shared::cluster.u64 %0, [%1];" : "=l"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void dsmem_st_u64(unsigned addr, unsigned long long v)
+{
+  asm volatile("st.shared::cluster.u64 [%0], %1;" ::"r"(addr), "l"(v) : "memory");
+}
+__device__ __forceinline__ void cluster_barrier()
+{
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(kSelectThreads)
+select_cluster_kernel(SelectArgs a, int csize)
+{
+  extern __shared__ unsigned long long selc_keys[];        // [kClusterKeys, padded]
+  __shared__ unsigned hist[256];
+  __shared__ unsigned merged[3][256];                       // CTA 0's copies are the cluster's (rotating)
+  __shared__ unsigned long long warp_tot[32];
+  __shared__ unsigned long long sh_prefix;
+  __shared__ unsigned sh_K, sh_bin, sh_ncand;
+  __shared__ unsigned long long cand[kSelectCand];          // CTA 0's
+  __shared__ unsigned long long cta_cnt[kMaxSelectCluster]; // CTA 0's: packed (greater << 32 | equal) per CTA
+  __shared__ unsigned long long fin[2];                     // CTA 0's: cutoff, ties to admit
+
+  const unsigned rank = blockIdx.x % (unsigned)csize;
+  const int row = a.row_begin + (int)(blockIdx.x / (unsigned)csize) * a.row_step;
+  const int s = blockIdx.y;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int B = 1 << a.logB;
+  const cplx *__restrict__ src =
+      a.xs + (long long)s * a.xs_stride + (long long)row * a.row_stride + (long long)rank * kClusterKeys;
+  unsigned long long *keys = selc_keys;
+  for (int i = tid; i < kClusterKeys; i += kSelectThreads)
+    keys[key_slot(i, true)] = (unsigned long long)__double_as_longlong(cabs2_rn(src[i]));
+  if (tid < 256) { merged[0][tid] = 0u; merged[1][tid] = 0u; merged[2][tid] = 0u; }
+  if (tid == 0) sh_ncand = 0u;
+  cluster_barrier();
+
+  const unsigned merged0 = map_to_rank(&merged[0][0], 0);
+  const int E = kClusterKeys / kSelectThreads;               // contiguous ownership: [tid*E, (tid+1)*E)
+  const int lo = tid * E;
+  unsigned long long prefix = 0;
+  unsigned K = (unsigned)a.num + 1u;
+  bool solo = false;               // candidates gathered in CTA 0, which finishes alone
+  int pass = 0;
+  for (; pass < 8 && !solo; pass++) {
+    const int shift = 56 - 8 * pass;
+    const unsigned mcur = merged0 + (unsigned)(pass % 3) * 256u * 4u;
+    if (tid < 256) hist[tid] = 0;
+    __syncthreads();
+    {
+      int run_d = -1;
+      unsigned run_c = 0;
+      for (int e = 0; e < E; e++) {
+        const unsigned long long key = keys[key_slot(lo + e, true)];
+        if (pass == 0 || (key >> (shift + 8)) == prefix) {
+          const int d = (int)((key >> shift) & 255ull);
+          if (d == run_d) {
+            run_c++;
+          } else {
+            if (run_c) atomicAdd(&hist[run_d], run_c);
+            run_d = d;
+            run_c = 1;
+          }
+        }
+      }
+      if (run_c) atomicAdd(&hist[run_d], run_c);
+    }
+    __syncthreads();
+    if (tid < 256) {
+      if (hist[tid]) dsmem_red_add(mcur + (unsigned)tid * 4u, hist[tid]);
+      // next pass's accumulator: last read in pass-2, i.e. before every CTA's previous barrier
+      if (rank == 0) merged[(pass + 1) % 3][tid] = 0u;
+    }
+    cluster_barrier();
+    if (warp == 0) {
+      // lane l owns bins 255-8l .. 248-8l, i.e. lanes ascend as keys descend
+      unsigned c8[8], tot = 0;
+#pragma unroll
+      for (int q = 0; q < 8; q++) {
+        c8[q] = dsmem_ld_u32(mcur + (unsigned)(255 - 8 * lane - q) * 4u);
+        tot += c8[q];
+      }
+      unsigned incl = tot;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const unsigned v = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += v;
+      }
+      const unsigned excl = incl - tot;
+      if (excl < K && K <= incl) {
+        unsigned run = excl;
+#pragma unroll
+        for (int q = 0; q < 8; q++) {
+          if (K <= run + c8[q]) {
+            sh_prefix = (prefix << 8) | (unsigned long long)(255 - 8 * lane - q);
+            sh_K = K - run;
+            sh_bin = c8[q];
+            break;
+          }
+          run += c8[q];
+        }
+      }
+    }
+    __syncthreads();
+    prefix = sh_prefix;
+    K = sh_K;
+    if (pass < 7 && sh_bin <= (unsigned)kSelectCand) {
+      // few keys still share the prefix: gather them in CTA 0
+      const unsigned ncand0 = map_to_rank(&sh_ncand, 0), cand0 = map_to_rank(&cand[0], 0);
+      for (int e = 0; e < E; e++) {
+        const unsigned long long key = keys[key_slot(lo + e, true)];
+        if ((key >> shift) == prefix) dsmem_st_u64(cand0 + dsmem_atom_add(ncand0, 1u) * 8u, key);
+      }
+      solo = true;
+    }
+  }
+  if (solo) {
+    cluster_barrier();                  // the candidates have landed in CTA 0
+    if (rank == 0) {
+      for (; pass < 8; pass++) {
+        const int shift = 56 - 8 * pass;
+        if (tid < 256) hist[tid] = 0;
+        __syncthreads();
+        if (tid < (int)sh_ncand) {
+          const unsigned long long key = cand[tid];
+          if ((key >> (shift + 8)) == prefix) atomicAdd(&hist[(int)((key >> shift) & 255ull)], 1u);
+        }
+        __syncthreads();
+        if (warp == 0) {
+          unsigned c8[8], tot = 0;
+#pragma unroll
+          for (int q = 0; q < 8; q++) {
+            c8[q] = hist[255 - 8 * lane - q];
+            tot += c8[q];
+          }
+          unsigned incl = tot;
+#pragma unroll
+          for (int off = 1; off < 32; off <<= 1) {
+            const unsigned v = __shfl_up_sync(0xffffffffu, incl, off);
+            if (lane >= off) incl += v;
+          }
+          const unsigned excl = incl - tot;
+          if (excl < K && K <= incl) {
+            unsigned run = excl;
+#pragma unroll
+            for (int q = 0; q < 8; q++) {
+              if (K <= run + c8[q]) {
+                sh_prefix = (prefix << 8) | (unsigned long long)(255 - 8 * lane - q);
+                sh_K = K - run;
+                break;
+              }
+              run += c8[q];
+            }
+          }
+        }
+        __syncthreads();
+        prefix = sh_prefix;
+        K = sh_K;
+      }
+    }
+  }
+  if (rank == 0 && tid == 0) { fin[0] = prefix; fin[1] = (unsigned long long)(K - 1u); }
+  cluster_barrier();
+  const unsigned fin0 = map_to_rank(&fin[0], 0);
+  const unsigned long long cutoff = dsmem_ld_u64(fin0);
+  const unsigned need = (unsigned)dsmem_ld_u64(fin0 + 8u);   // ties at the cutoff to admit, in index order
+
+  // per-thread counts over the owned chunk, packed (gt << 32 | eq); block scan; CTA totals to CTA 0
+  unsigned long long cnt = 0;
+  for (int e = 0; e < E; e++) {
+    const unsigned long long key = keys[key_slot(lo + e, true)];
+    cnt += key > cutoff ? (1ull << 32) : (key == cutoff ? 1ull : 0ull);
+  }
+  unsigned long long incl = cnt;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const unsigned long long v = __shfl_up_sync(0xffffffffu, incl, off);
+    if (lane >= off) incl += v;
+  }
+  if (lane == 31) warp_tot[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const unsigned long long t = warp_tot[lane];
+    unsigned long long sc = t;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+      const unsigned long long v = __shfl_up_sync(0xffffffffu, sc, off);
+      if (lane >= off) sc += v;
+    }
+    warp_tot[lane] = sc - t;     // exclusive prefix of warp totals
+    if (lane == 31) dsmem_st_u64(map_to_rank(&cta_cnt[0], 0) + rank * 8u, sc);
+  }
+  cluster_barrier();
+  unsigned long long base = 0;
+  {
+    const unsigned cnt0 = map_to_rank(&cta_cnt[0], 0);
+    for (unsigned q = 0; q < rank; q++) base += dsmem_ld_u64(cnt0 + q * 8u);
+  }
+  const unsigned long long before = base + warp_tot[warp] + incl - cnt;
+  unsigned gt_b = (unsigned)(before >> 32), eq_b = (unsigned)(before & 0xffffffffu);
+  const int words = B / 32;
+  int *J = a.J + (long long)s * a.J_sig_stride + (long long)row * a.num;
+  unsigned *bm = a.bitmap + (long long)s * a.bm_sig_stride + (long long)row * words + rank * (kClusterKeys / 32);
+  // E = 16 consecutive buckets per thread: two threads share a bitmap word
+  unsigned bits = 0;
+  for (int e = 0; e < E; e++) {
+    const int i = lo + e;
+    const unsigned long long key = keys[key_slot(i, true)];
+    const bool f_gt = key > cutoff, f_eq = key == cutoff;
+    if (f_gt || (f_eq && eq_b < need)) {
+      J[gt_b + (eq_b < need ? eq_b : need)] = (int)(rank * kClusterKeys) + i;
+      bits |= 1u << (i & 31);
+    }
+    gt_b += f_gt;
+    eq_b += f_eq;
+  }
+  const unsigned other = __shfl_xor_sync(0xffffffffu, bits, 1);
+  if ((tid & 1) == 0) bm[lo >> 5] = bits | other;
+  // no CTA may exit while another still reads its shared memory
+  cluster_barrier();
+}
+
+static size_t select_cluster_smem_bytes() { return (size_t)(kClusterKeys + (kClusterKeys >> 4) + 1) * 8; }
+
+// one cluster of B/16384 CTAs per row; false if this device will not take the launch
+static bool launch_select_cluster(const SelectArgs &a, int nrows, int nsig, cudaStream_t st)
+{
+  const int B = 1 << a.logB;
+  const int csize = B / kClusterKeys;
+  if (csize < 2 || csize > kMaxSelectCluster) return false;
+  static int usable = -1;     // -1 unknown, 0 no, 1 yes
+  if (usable == 0) return false;
+  const size_t smem = select_cluster_smem_bytes();
+  if (usable < 0) {
+    if (cudaFuncSetAttribute(select_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess ||
+        cudaFuncSetAttribute(select_cluster_kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) != cudaSuccess) {
+      cudaGetLastError();
+      usable = 0;
+      return false;
+    }
+  }
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3((unsigned)(nrows * csize), (unsigned)nsig);
+  cfg.blockDim = dim3(kSelectThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)csize;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (usable < 0) {
+    int nclusters = 0;
+    if (cudaOccupancyMaxActiveClusters(&nclusters, select_cluster_kernel, &cfg) != cudaSuccess || nclusters < 1) {
+      cudaGetLastError();
+      usable = 0;
+      return false;
+    }
+    usable = 1;
+  }
+  if (cudaLaunchKernelEx(&cfg, select_cluster_kernel, a, csize) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  g_launches++;
+  return true;
+}
+
 static size_t select_smem_bytes(int B, bool keys_in_smem)
 {
   const int words = B >= 32 ? B / 32 : 1;
@@ -631,6 +837,7 @@ int launch_select(const SelectArgs &a, int nrows, int nsig, cudaStream_t st)
       set_error("launch_select: rows above 16384 buckets need the global key scratch");
       return -1;
     }
+    if (!getenv("SFFTB_NO_SELECT_CLUSTER") && launch_select_cluster(a, nrows, nsig, st)) return 0;
     return launch_select_big(a, nrows, nsig, st);
   }
   SFFTB_ONCE_PER_DEVICE(SFFTB_CUDA(cudaFuncSetAttribute(select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

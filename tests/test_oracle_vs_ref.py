@@ -108,3 +108,27 @@ def test_v3_restatement_bit_identical_to_reference(oracle_mod, ref_mod, n, k, s4
     out = subprocess.run([sys.executable, "-c", _V3_CHILD, ROOT, str(n), str(k), str(s48), str(sx)],
                          capture_output=True, text=True, timeout=600)
     assert "V3_BITEXACT" in out.stdout, out.stdout + out.stderr
+
+
+def test_mkl_backed_timing_build_against_numpy(ref_mod):
+    """The CPU TIMING baseline links the unmodified reference over MKL DFTI (oracle/shim/
+    fftw_shim_mkl.c; DFTI comes from PyTorch's libtorch_cpu.so, its constants are declared by
+    hand).  Before it is allowed to time anything: its DFTs must agree with numpy.fft, forward
+    and backward, power-of-two and odd lengths (the reference's window DFT, src/filters.cc:81),
+    and a transform through it must recover the planted spectrum."""
+    if not ref_mod.available("mkl") or not ref_mod.mkl_provider():
+        pytest.skip("libsfft_ref_mkl.so / libtorch_cpu.so not available")
+    rng = np.random.default_rng(0)
+    for n in (8, 1024, 7507, 27853, 1 << 16):
+        x = rng.standard_normal(n) + 1j * rng.standard_normal(n)
+        f = ref_mod.fftw_dft(x, backwards=False, kind="mkl")
+        b = ref_mod.fftw_dft(x, backwards=True, kind="mkl")
+        assert np.abs(f - np.fft.fft(x)).max() <= 1e-12 * np.abs(f).max()
+        assert np.abs(b - np.fft.ifft(x) * n).max() <= 1e-12 * np.abs(b).max()
+    n, k = 65536, 50
+    x, xf = ref_mod.generate_input(n, k, 5, kind="mkl")
+    p = ref_mod.RefPlan(n, k, 1, kind="mkl")
+    p.seed(17, 3)
+    out = p.exec(x)
+    true = np.flatnonzero(xf)
+    assert np.abs(out[true] - xf[true]).max() < 1e-4

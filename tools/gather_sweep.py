@@ -34,11 +34,11 @@ def main():
     info = plan.info()
     samples = batch * (info["gather_samples"] - (info["Comb_loops"] * info["W_Comb"] if version == 2 else 0))
     plan.stage_timing(True)
-    settings = [("grid", u, 0) for u in (4, 8)] + [("persist", u, c) for u in (4, 8) for c in (2, 3, 4, 5)]
-    for mode, unroll, ctas in settings:
-        os.environ["SFFTB_GATHER_MODE"] = mode
+    # dynamic shared memory per CTA caps the resident CTAs per SM: 0 (registers decide), 56 KB (4), 75 KB (3), 113 KB (2)
+    settings = [(u, pad) for u in (2, 4, 8) for pad in (0, 56 * 1024, 75 * 1024, 113 * 1024)]
+    for unroll, pad in settings:
         os.environ["SFFTB_GATHER_UNROLL"] = str(unroll)
-        os.environ["SFFTB_GATHER_CTAS"] = str(ctas)
+        os.environ["SFFTB_GATHER_SMEM"] = str(pad)
         acc = []
         for i in range(reps + 2):
             flush.zero_()
@@ -50,7 +50,7 @@ def main():
             if i >= 2:
                 acc.append(t["gather"])
         g = sum(acc) / len(acc)
-        print(json.dumps({"workload": wl, "mode": mode, "unroll": unroll, "ctas_per_sm": ctas, "gather_ms": g,
+        print(json.dumps({"workload": wl, "unroll": unroll, "smem_pad": pad, "gather_ms": g,
                           "min_ms": min(acc), "gsamples_gathered_per_s": samples / (g * 1e-3) / 1e9}), flush=True)
     plan.close()
 
