@@ -682,9 +682,12 @@ def run_ours(args):
             # the legacy path moves 16 n bytes in and 16 n bytes out per transform
             e2e_gbs = e2e_value * 1e9 * 32 / 1e9
             line["e2e"]["host_link_gbs_used"] = e2e_gbs
-            line["e2e"]["host_link_gbs_measured_ceiling"] = probe["duplex_gbs_aggregate"]
-            line["e2e"]["note"] = ("bytes moved over the host link per second by the e2e run vs what N ranks copying "
-                                   "concurrently (pcie_probe, full duplex) reach on this box")
+            line["e2e"]["host_link_gbs_one_way_ceiling"] = probe["h2d_only_gbs_aggregate"]
+            line["e2e"]["host_link_gbs_duplex_ceiling"] = probe["duplex_gbs_aggregate"]
+            line["e2e"]["note"] = ("bytes moved over the host link per second by the e2e run vs what the N ranks reach "
+                                   "copying concurrently on this box (pcie_probe). v2's result is dense, so its input "
+                                   "and output copies cannot overlap: the one-way figure is its ceiling; v1/v3 stream "
+                                   "the zero fill out while the input streams in (duplex)")
         if world == 1 and not args.no_cpu_baseline:
             try:
                 line["cpu_baseline"] = cpu_reference_run(args.workload, min(batch, 8), 1, 0, budget_s=90.0)

@@ -870,9 +870,10 @@ constexpr int kVoteMaxLoops = 8;        // location loops kept in registers; mor
 
 template <bool SMEM_MAPS>
 __global__ void __launch_bounds__(kVoteThreads)
-vote_kernel(LoopGeom g, VoteArgs a, int first_loops)
+vote_kernel(LoopGeom g, VoteArgs a, int first_loops, int entries_per_cta)
 {
   extern __shared__ unsigned vote_bm[];          // [loops_loc][words] when SMEM_MAPS
+  __shared__ unsigned s_a[kVoteMaxLoops];        // a_j of the candidate-generating loops
   const int s = blockIdx.y;
   const int logB = g.logB[0];
   const int logseg = g.logn - logB;
@@ -881,10 +882,11 @@ vote_kernel(LoopGeom g, VoteArgs a, int first_loops)
   const int words = logB >= 5 ? (1 << (logB - 5)) : 1;
   const int L = g.loops_loc;
   const unsigned *gbm = a.bitmap + (long long)s * a.bm_sig_stride;
-  if (SMEM_MAPS) {
+  if (SMEM_MAPS)
     for (int i = threadIdx.x; i < L * words; i += kVoteThreads) vote_bm[i] = gbm[i];
-    __syncthreads();
-  }
+  if (threadIdx.x < kVoteMaxLoops)
+    s_a[threadIdx.x] = threadIdx.x < L ? (unsigned)a.perm[(long long)s * perm_stride(g.loops) + threadIdx.x] : 0u;
+  __syncthreads();
   const unsigned *bm = SMEM_MAPS ? vote_bm : gbm;
   unsigned ai[kVoteMaxLoops];
 #pragma unroll
@@ -892,34 +894,41 @@ vote_kernel(LoopGeom g, VoteArgs a, int first_loops)
     ai[q] = q < L ? (unsigned)a.perm[(long long)s * perm_stride(g.loops) + g.loops + q] : 0u;
   const unsigned *cb = a.comb_bitmap ? a.comb_bitmap + (long long)s * a.comb_sig_stride : nullptr;
 
-  // a CTA may own several (loop, entry) pairs when the grid was capped
-  for (int e = blockIdx.x; e < first_loops * a.num; e += gridDim.x) {
-    const int j = e / a.num, Ji = e - j * a.num;
-    const unsigned Jv = (unsigned)a.J[(long long)s * a.J_sig_stride + (long long)j * a.num + Ji];
+  // this CTA's (loop, entry) pairs, flattened with their n/B positions: every thread walks
+  // candidates of several entries, so the entries' dependent loads overlap
+  const int total_entries = first_loops * a.num;
+  const int e0 = blockIdx.x * entries_per_cta;
+  const int e1 = e0 + entries_per_cta < total_entries ? e0 + entries_per_cta : total_entries;
+  const unsigned ncand = (unsigned)(e1 - e0) << logseg;
+  const int *Jrow = a.J + (long long)s * a.J_sig_stride;
+  int j = e0 / a.num;                              // loops of consecutive entries only ever increase
+  for (unsigned c = threadIdx.x; c < ncand; c += kVoteThreads) {
+    const int e = e0 + (int)(c >> logseg);
+    const unsigned t = c & (seg - 1u);
+    while (e >= (j + 1) * a.num) j++;
+    // J is [loops_loc][num]; entry e of the flattened list is J[j][e - j*num], i.e. J[e]
+    const unsigned Jv = (unsigned)__ldg(&Jrow[e]);
     // cf12.cc:102: low = ceil((J - 0.5) * n/B) mod n  == J*seg - seg/2 (exact for seg >= 2)
     const unsigned low = ((Jv << logseg) - half) & mask;
-    const unsigned aj = (unsigned)a.perm[(long long)s * perm_stride(g.loops) + j];
-    for (unsigned t = threadIdx.x; t < seg; t += kVoteThreads) {
-      const unsigned p = (low + t) & mask;
-      const unsigned loc = (aj * p) & mask;                       // n is a power of two <= 2^31
-      const unsigned rres = loc & (unsigned)a.W_mask;              // v2: loc mod W_Comb must be approved
-      if (cb && !((__ldg(&cb[rres >> 5]) >> (rres & 31u)) & 1u)) continue;
-      // emitted by the first loop that votes for it; score = votes over all location loops
-      bool earlier = false;
-      int score = 1;
+    const unsigned p = (low + t) & mask;
+    const unsigned loc = (s_a[j] * p) & mask;                     // n is a power of two <= 2^31
+    const unsigned rres = loc & (unsigned)a.W_mask;              // v2: loc mod W_Comb must be approved
+    if (cb && !((__ldg(&cb[rres >> 5]) >> (rres & 31u)) & 1u)) continue;
+    // emitted by the first loop that votes for it; score = votes over all location loops
+    bool earlier = false;
+    int score = 1;
 #pragma unroll
-      for (int q = 0; q < kVoteMaxLoops; q++) {
-        if (q < L && q != j) {
-          const unsigned Jb = ((((ai[q] * loc) & mask) + half) >> logseg) & Bm;
-          const bool v = (bm[q * words + (Jb >> 5)] >> (Jb & 31u)) & 1u;
-          if (q < j) earlier |= v;
-          else score += v ? 1 : 0;
-        }
+    for (int q = 0; q < kVoteMaxLoops; q++) {
+      if (q < L && q != j) {
+        const unsigned Jb = ((((ai[q] * loc) & mask) + half) >> logseg) & Bm;
+        const bool v = (bm[q * words + (Jb >> 5)] >> (Jb & 31u)) & 1u;
+        if (q < j) earlier |= v;
+        else score += v ? 1 : 0;
       }
-      if (!earlier && score >= a.thresh) {
-        const int pos = atomicAdd(&a.count[s], 1);
-        if (pos < a.hits_cap) a.hits[(long long)s * a.hits_cap + pos] = (int)loc;
-      }
+    }
+    if (!earlier && score >= a.thresh) {
+      const int pos = atomicAdd(&a.count[s], 1);
+      if (pos < a.hits_cap) a.hits[(long long)s * a.hits_cap + pos] = (int)loc;
     }
   }
 }
@@ -968,17 +977,23 @@ int launch_vote(const LoopGeom &g, const VoteArgs &a, int nsig, cudaStream_t st)
   const int first_loops = g.loops_loc - a.thresh + 1;
   if (first_loops <= 0) return 0;
   const int words = g.logB[0] >= 5 ? (1 << (g.logB[0] - 5)) : 1;
-  long long blocks = (long long)first_loops * a.num;
-  const long long share = 148ll * 64 / (nsig < 64 ? nsig : 64);
-  const long long cap = share > 148 ? share : 148;
-  if (blocks > cap) blocks = cap;
-  dim3 grid((unsigned)blocks, (unsigned)nsig);
+  const long long entries = (long long)first_loops * a.num;
   if (g.loops_loc > kVoteMaxLoops) {
-    vote_generic_kernel<<<grid, kVoteThreads, 0, st>>>(g, a, first_loops);
+    long long blocks = entries;
+    const long long share = 148ll * 64 / (nsig < 64 ? nsig : 64);
+    const long long cap = share > 148 ? share : 148;
+    if (blocks > cap) blocks = cap;
+    vote_generic_kernel<<<dim3((unsigned)blocks, (unsigned)nsig), kVoteThreads, 0, st>>>(g, a, first_loops);
   } else {
+    // ~32 candidates per thread: 8192 candidates = 8192 / (n/B) entries per CTA
+    const int logseg = g.logn - g.logB[0];
+    int per_cta = logseg >= 13 ? 1 : (8192 >> logseg);
+    if (per_cta > entries) per_cta = (int)entries;
+    const long long blocks = (entries + per_cta - 1) / per_cta;
+    const dim3 grid((unsigned)blocks, (unsigned)nsig);
     const size_t smem = sizeof(unsigned) * (size_t)g.loops_loc * words;
-    if (smem <= 48 * 1024) vote_kernel<true><<<grid, kVoteThreads, smem, st>>>(g, a, first_loops);
-    else vote_kernel<false><<<grid, kVoteThreads, 0, st>>>(g, a, first_loops);
+    if (smem <= 48 * 1024) vote_kernel<true><<<grid, kVoteThreads, smem, st>>>(g, a, first_loops, per_cta);
+    else vote_kernel<false><<<grid, kVoteThreads, 0, st>>>(g, a, first_loops, per_cta);
   }
   SFFTB_LAUNCH_CHECK();
   return 0;
