@@ -630,11 +630,32 @@ def run_ours(args):
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s"
 
-        traffic = {}
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json"))).get(args.workload, {})
-        except Exception:
-            pass
+        # DRAM bytes per launch of each stage's kernels: ncu capture of THIS source tree
+        # (tools/make_traffic.py over `ncu --set full` exports, committed per round)
+        traffic, traffic_file = {}, None
+        for cand in ("r02_traffic.json",):
+            try:
+                traffic = json.load(open(os.path.join(ROOT, "profiles", cand))).get(args.workload, {}) \
+                    .get("per_stage_dram_bytes", {})
+                traffic_file = "profiles/" + cand
+                break
+            except Exception:
+                pass
+        notes = {
+            "estimate": ("v2_regroup_kernel + v2_fused_kernel: DRAM traffic equals the algorithmic bytes (spectra in, "
+                         "result list out); bound by instruction issue on the ALU select pipe (two medians of 20: 540 "
+                         "FSEL + 154 DSETP per coefficient) and the FP64 pipe (40 exact divisions): 76 % of the floor "
+                         "those pipes set for this instruction mix -- DESIGN.md K7', profiles/r02_C2_full.txt, "
+                         "profiles/r02_pipe_overlap.jsonl") if version == 2 else None,
+            "gather": ("bound by the random-REQUEST rate of HBM, not its bandwidth: 16-byte samples at a random odd "
+                       "stride, one per 32-byte sector (sector efficiency 50 % on the signal stream, the ceiling); "
+                       "profiles/r02_gather_ab.md"),
+            "peel": "one thread-block cluster per signal; a chain of ~40 dependent steps (global round trips, "
+                    "double-precision libm latency), not a bandwidth-bound kernel -- DESIGN.md 5",
+        }
+        # random 16-byte reads per second the memory system sustains with nothing else in the kernel
+        # (tools/microbench/ld_variants under ncu, profiles/r02_ld_variants_*: 72.6 G/s over 256 MiB, 39 G/s over 2 GiB)
+        req_ceiling = 72.6e9 if n * 16 <= (256 << 20) else 39e9
 
         def roof(stage):
             ms = stages.get(stage)
@@ -643,12 +664,19 @@ def run_ours(args):
             b = batch * stage_bytes(info, stage, count)
             ach = b / (ms * 1e-3) / 1e9
             r = {"kernel": stage, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                 "frac": ach / hbm_peak, "traffic": traffic.get(stage), "ms": ms, "algorithmic_bytes": b,
-                 "peak_source": peak_src,
-                 "traffic_source": "ncu dram bytes per launch, profiles/r01_traffic.json" if stage in traffic else None}
-            note = traffic.get(stage + "_note")
-            if note:
-                r["note"] = note
+                 "frac": ach / hbm_peak, "traffic": (batch * traffic[stage]) if stage in traffic else None,
+                 "ms": ms, "algorithmic_bytes": b, "peak_source": peak_src,
+                 "traffic_source": ("ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, " + traffic_file)
+                 if stage in traffic else None}
+            if notes.get(stage):
+                r["note"] = notes[stage]
+            if stage == "gather" and batch == 1:
+                samples = info["gather_samples"] - (info["Comb_loops"] * info["W_Comb"] if version == 2 else 0)
+                rate = samples / (ms * 1e-3)
+                r["random_requests_per_s"] = rate
+                r["random_request_ceiling_per_s"] = req_ceiling
+                r["frac_of_request_ceiling"] = rate / req_ceiling
+                r["sector_efficiency_signal_stream"] = 0.5
             return r
 
         dominant = max(stages, key=stages.get) if stages else None

@@ -74,7 +74,7 @@ def build(force=False, verbose=False):
     if failed:
         raise RuntimeError("libsfft.so: compilation failed")
     link = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", HOST_CXX,
-            "-o", OUT] + objs + ["-lm"]
+            "-o", OUT] + objs + ["-lm", "-lpthread"]
     subprocess.check_call(link)
     if not VARIANT:
         build_tools()

@@ -37,6 +37,8 @@ double sfftb_host_cabs(double re, double im);
 }
 
 #include <chrono>
+#include <string.h>
+#include <thread>
 
 namespace sfftb {
 
@@ -249,6 +251,155 @@ __global__ void peak_candidates_kernel(const cplx *__restrict__ H, int logn, con
   }
 }
 
+// ---- the same two recurrences on HOST threads ---------------------------------------------
+// A dependent chain of n double-precision additions is ~30 ns a step on one GPU thread and
+// ~1.5 ns on a host core; at n = 2^27 the device chains were 96 % of the plan time.  For
+// large n each chain runs on its own host thread, streaming through two pinned staging
+// buffers (download window -> add in order -> upload), so copies hide under the arithmetic.
+// Same operations, same order, one rounding each (host code is built with -ffp-contract=off).
+constexpr long long kHostChunk = 1ll << 21;            // elements per staging buffer (32 MiB)
+
+struct HostChainResult {
+  int rc = 0;
+  double qmax = 0.0;
+};
+
+static bool host_chains_wanted(int logn)
+{
+  if (const char *e = getenv("SFFTB_HOST_CHAINS")) return atoi(e) != 0;
+  return logn >= 24;
+}
+
+#define CHAIN_CUDA(call) do { if ((call) != cudaSuccess) { res->rc = -1; goto done; } } while (0)
+
+// filters.cc:134-140
+static void ramp_host_chain(int device, int logn, double step_re, double step_im, cplx *d_R, HostChainResult *res)
+{
+  const long long n = 1ll << logn;
+  const long long C = n < kHostChunk ? n : kHostChunk;
+  cplx *h[2] = {nullptr, nullptr};
+  cudaEvent_t ev[2] = {nullptr, nullptr};
+  cudaStream_t st = nullptr;
+  double cr = 1.0, ci = 0.0;
+  CHAIN_CUDA(cudaSetDevice(device));
+  CHAIN_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+  for (int k = 0; k < 2; k++) {
+    CHAIN_CUDA(cudaHostAlloc(&h[k], sizeof(cplx) * C, cudaHostAllocDefault));
+    CHAIN_CUDA(cudaEventCreateWithFlags(&ev[k], cudaEventDisableTiming));
+  }
+  for (long long base = 0, k = 0; base < n; base += C, k ^= 1) {
+    CHAIN_CUDA(cudaEventSynchronize(ev[k]));
+    cplx *o = h[k];
+    const long long cnt = n - base < C ? n - base : C;
+    for (long long e = 0; e < cnt; e++) {
+      o[e].x = cr; o[e].y = ci;
+      const double nr = cr * step_re - ci * step_im;
+      const double ni = cr * step_im + ci * step_re;
+      cr = nr; ci = ni;
+    }
+    CHAIN_CUDA(cudaMemcpyAsync(d_R + base, o, sizeof(cplx) * cnt, cudaMemcpyHostToDevice, st));
+    CHAIN_CUDA(cudaEventRecord(ev[k], st));
+  }
+  CHAIN_CUDA(cudaStreamSynchronize(st));
+done:
+  for (int k = 0; k < 2; k++) {
+    if (h[k]) cudaFreeHost(h[k]);
+    if (ev[k]) cudaEventDestroy(ev[k]);
+  }
+  if (st) cudaStreamDestroy(st);
+}
+
+// copy `cnt` elements starting at index `start` (mod n) of a device array of n elements
+static cudaError_t copy_ring(cplx *host, cplx *dev, long long n, long long start, long long cnt, bool to_host,
+                             cudaStream_t st)
+{
+  start &= n - 1;
+  const long long first = cnt < n - start ? cnt : n - start;
+  cudaError_t e = to_host ? cudaMemcpyAsync(host, dev + start, sizeof(cplx) * first, cudaMemcpyDeviceToHost, st)
+                          : cudaMemcpyAsync(dev + start, host, sizeof(cplx) * first, cudaMemcpyHostToDevice, st);
+  if (e != cudaSuccess || first == cnt) return e;
+  return to_host ? cudaMemcpyAsync(host + first, dev, sizeof(cplx) * (cnt - first), cudaMemcpyDeviceToHost, st)
+                 : cudaMemcpyAsync(dev, host + first, sizeof(cplx) * (cnt - first), cudaMemcpyHostToDevice, st);
+}
+
+// filters.cc:119-130:  s = sum_{i<b} g[i];  for i: h[(i+b/2)%n] = s;  s = s + (g[(i+b)%n] - g[i])
+static void boxcar_host_chain(int device, int logn, int b, cplx *d_G, cplx *d_H, HostChainResult *res)
+{
+  const long long n = 1ll << logn;
+  const long long C = n < kHostChunk ? n : kHostChunk;
+  const long long win = C + b;                          // chunk i needs g[base .. base + C + b)
+  const long long off = b / 2;
+  cplx *hin[2] = {nullptr, nullptr}, *hout[2] = {nullptr, nullptr};
+  cudaEvent_t evd[2] = {nullptr, nullptr}, evu[2] = {nullptr, nullptr};
+  cudaStream_t sd = nullptr, su = nullptr;
+  double sr = 0.0, si = 0.0, qmax = 0.0;
+  const long long nchunks = (n + C - 1) / C;
+  CHAIN_CUDA(cudaSetDevice(device));
+  CHAIN_CUDA(cudaStreamCreateWithFlags(&sd, cudaStreamNonBlocking));
+  CHAIN_CUDA(cudaStreamCreateWithFlags(&su, cudaStreamNonBlocking));
+  for (int k = 0; k < 2; k++) {
+    CHAIN_CUDA(cudaHostAlloc(&hin[k], sizeof(cplx) * win, cudaHostAllocDefault));
+    CHAIN_CUDA(cudaHostAlloc(&hout[k], sizeof(cplx) * C, cudaHostAllocDefault));
+    CHAIN_CUDA(cudaEventCreateWithFlags(&evd[k], cudaEventDisableTiming));
+    CHAIN_CUDA(cudaEventCreateWithFlags(&evu[k], cudaEventDisableTiming));
+  }
+  // :121-124, the first b elements in order (b can exceed a staging buffer)
+  for (long long base = 0; base < b; base += C) {
+    const long long cnt = b - base < C ? b - base : C;
+    CHAIN_CUDA(copy_ring(hin[0], d_G, n, base, cnt, true, sd));
+    CHAIN_CUDA(cudaStreamSynchronize(sd));
+    for (long long e = 0; e < cnt; e++) { sr = sr + hin[0][e].x; si = si + hin[0][e].y; }
+  }
+  CHAIN_CUDA(copy_ring(hin[0], d_G, n, 0, win < n ? win : n, true, sd));
+  CHAIN_CUDA(cudaEventRecord(evd[0], sd));
+  for (long long c = 0; c < nchunks; c++) {
+    const int k = (int)(c & 1);
+    const long long base = c * C;
+    const long long cnt = n - base < C ? n - base : C;
+    if (c + 1 < nchunks) {
+      // the next window goes into the other buffer, whose chunk has been consumed already
+      CHAIN_CUDA(copy_ring(hin[k ^ 1], d_G, n, base + C, win < n ? win : n, true, sd));
+      CHAIN_CUDA(cudaEventRecord(evd[k ^ 1], sd));
+    }
+    CHAIN_CUDA(cudaEventSynchronize(evd[k]));
+    CHAIN_CUDA(cudaEventSynchronize(evu[k]));
+    const cplx *g = hin[k];
+    cplx *o = hout[k];
+    if (win <= n) {
+      for (long long e = 0; e < cnt; e++) {
+        o[e].x = sr; o[e].y = si;
+        const double q = sr * sr + si * si;
+        qmax = q > qmax ? q : qmax;
+        const double dr = g[e + b].x - g[e].x, di = g[e + b].y - g[e].y;
+        sr = sr + dr; si = si + di;
+      }
+    } else {
+      // tiny n (only reachable through SFFTB_HOST_CHAINS=1): the window wraps inside the buffer
+      for (long long e = 0; e < cnt; e++) {
+        o[e].x = sr; o[e].y = si;
+        const double q = sr * sr + si * si;
+        qmax = q > qmax ? q : qmax;
+        const cplx in = g[(e + b) & (n - 1)], out = g[e];
+        sr = sr + (in.x - out.x); si = si + (in.y - out.y);
+      }
+    }
+    CHAIN_CUDA(copy_ring(o, d_H, n, base + off, cnt, false, su));
+    CHAIN_CUDA(cudaEventRecord(evu[k], su));
+  }
+  CHAIN_CUDA(cudaStreamSynchronize(su));
+  res->qmax = qmax;
+done:
+  for (int k = 0; k < 2; k++) {
+    if (hin[k]) cudaFreeHost(hin[k]);
+    if (hout[k]) cudaFreeHost(hout[k]);
+    if (evd[k]) cudaEventDestroy(evd[k]);
+    if (evu[k]) cudaEventDestroy(evu[k]);
+  }
+  if (sd) cudaStreamDestroy(sd);
+  if (su) cudaStreamDestroy(su);
+}
+#undef CHAIN_CUDA
+
 // filters.cc:134-140:  offsetc = 1;  for i: ramp[i] = offsetc;  offsetc *= step
 __global__ void __launch_bounds__(kSeqThreads)
 ramp_sequential_kernel(int logn, double step_re, double step_im, cplx *R)
@@ -351,6 +502,8 @@ struct WindowWork {
   cplx *d_G = nullptr;      // FFT_n of the centred window
   cplx *d_R = nullptr;      // ramp step^i
   cudaStream_t ramp_stream = nullptr;
+  std::thread *ramp_thread = nullptr;      // host chain (large n)
+  HostChainResult ramp_res;
 };
 
 int build_window(int logn, WindowWork *ww, const Twiddles &twn, cudaStream_t st)
@@ -373,8 +526,14 @@ int build_window(int logn, WindowWork *ww, const Twiddles &twn, cudaStream_t st)
   SFFTB_CUDA(cudaMalloc(&ww->d_R, sizeof(cplx) * n));
   // the phase ramp does not depend on the data: start its chain on its own stream now
   SFFTB_CUDA(cudaStreamCreateWithFlags(&ww->ramp_stream, cudaStreamNonBlocking));
-  ramp_sequential_kernel<<<1, kSeqThreads, 0, ww->ramp_stream>>>(logn, step_re, step_im, ww->d_R);
-  SFFTB_LAUNCH_CHECK();
+  if (host_chains_wanted(logn)) {
+    int device = 0;
+    SFFTB_CUDA(cudaGetDevice(&device));
+    ww->ramp_thread = new std::thread(ramp_host_chain, device, logn, step_re, step_im, ww->d_R, &ww->ramp_res);
+  } else {
+    ramp_sequential_kernel<<<1, kSeqThreads, 0, ww->ramp_stream>>>(logn, step_re, step_im, ww->d_R);
+    SFFTB_LAUNCH_CHECK();
+  }
 
   SFFTB_CUDA(cudaMemcpyAsync(d_samples, samples.data(), sizeof(cplx) * w, cudaMemcpyHostToDevice, st));
   // w-point DFT by Bluestein (filters.cc:81), rotate, keep the real part
@@ -476,11 +635,35 @@ int build_filters(int logn, int count, const FilterSpec *specs, DeviceFilter **o
     SFFTB_CUDA(cudaMalloc(&outs[f]->time, sizeof(cplx) * outs[f]->w));
     SFFTB_CUDA(cudaMalloc(&outs[f]->fwin, sizeof(cplx) * (2ll * specs[f].fw_half + 1)));
   }
+  const bool host_chains = host_chains_wanted(logn);
+  std::thread *box_thread[2] = {nullptr, nullptr};
+  HostChainResult box_res[2];
+  if (host_chains) {
+    int device = 0;
+    SFFTB_CUDA(cudaGetDevice(&device));
+    for (int f = 0; f < count; f++)
+      box_thread[f] = new std::thread(boxcar_host_chain, device, logn, specs[f].b, win[which_win[f]].d_G, d_H[f], &box_res[f]);
+  }
   for (int f = 0; f < count; f++) {
-    SFFTB_CUDA(cudaMemsetAsync(d_maxq[f], 0, sizeof(unsigned long long), fs[f]));
     SFFTB_CUDA(cudaMemsetAsync(d_ncand[f], 0, sizeof(int), fs[f]));
-    boxcar_sequential_kernel<<<1, kSeqThreads, 0, fs[f]>>>(win[which_win[f]].d_G, logn, specs[f].b, d_H[f], d_maxq[f]);
-    SFFTB_LAUNCH_CHECK();
+    if (host_chains) {
+      box_thread[f]->join();
+      delete box_thread[f];
+      box_thread[f] = nullptr;
+      if (box_res[f].rc) {
+        for (int q = f + 1; q < count; q++) { box_thread[q]->join(); delete box_thread[q]; }
+        set_error("build_filter: the host boxcar chain failed (CUDA error in its staging copies)");
+        return -1;
+      }
+      unsigned long long bits;
+      memcpy(&bits, &box_res[f].qmax, sizeof bits);
+      SFFTB_CUDA(cudaMemcpyAsync(d_maxq[f], &bits, sizeof bits, cudaMemcpyHostToDevice, fs[f]));
+      SFFTB_CUDA(cudaStreamSynchronize(fs[f]));
+    } else {
+      SFFTB_CUDA(cudaMemsetAsync(d_maxq[f], 0, sizeof(unsigned long long), fs[f]));
+      boxcar_sequential_kernel<<<1, kSeqThreads, 0, fs[f]>>>(win[which_win[f]].d_G, logn, specs[f].b, d_H[f], d_maxq[f]);
+      SFFTB_LAUNCH_CHECK();
+    }
     peak_candidates_kernel<<<grid_for(n), kT, 0, fs[f]>>>(d_H[f], logn, d_maxq[f], d_cand[f], d_ncand[f], cand_cap);
     SFFTB_LAUNCH_CHECK();
   }
@@ -498,6 +681,13 @@ int build_filters(int logn, int count, const FilterSpec *specs, DeviceFilter **o
     for (int i = 0; i < ncand; i++) {
       const double m = sfftb_host_cabs(cand[(size_t)i].x, cand[(size_t)i].y);
       if (m > peak) peak = m;
+    }
+    if (win[which_win[f]].ramp_thread) {
+      WindowWork &wr = win[which_win[f]];
+      wr.ramp_thread->join();
+      delete wr.ramp_thread;
+      wr.ramp_thread = nullptr;
+      if (wr.ramp_res.rc) { set_error("build_filter: the host ramp chain failed"); return -1; }
     }
     SFFTB_CUDA(cudaStreamSynchronize(ww.ramp_stream));
     // the spectrum G of the window is no longer needed once every boxcar over it has run;

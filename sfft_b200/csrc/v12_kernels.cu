@@ -867,6 +867,7 @@ int launch_select(const SelectArgs &a, int nrows, int nsig, cudaStream_t st)
 // a flat index were most of the old kernel's instructions.
 constexpr int kVoteThreads = 256;
 constexpr int kVoteMaxLoops = 8;        // location loops kept in registers; more -> generic path
+constexpr int kVoteHitCap = 2048;       // hits a CTA collects in shared memory before it falls back to global atomics
 
 template <bool SMEM_MAPS>
 __global__ void __launch_bounds__(kVoteThreads)
@@ -874,6 +875,10 @@ vote_kernel(LoopGeom g, VoteArgs a, int first_loops, int entries_per_cta)
 {
   extern __shared__ unsigned vote_bm[];          // [loops_loc][words] when SMEM_MAPS
   __shared__ unsigned s_a[kVoteMaxLoops];        // a_j of the candidate-generating loops
+  // hits of this CTA, appended to the global list with ONE atomic: thousands of atomics on one
+  // signal's counter serialise in L2 (~3 ns each), which was most of a batch's voting time
+  __shared__ int s_hits[kVoteHitCap];
+  __shared__ int s_nhit, s_base;
   const int s = blockIdx.y;
   const int logB = g.logB[0];
   const int logseg = g.logn - logB;
@@ -886,6 +891,7 @@ vote_kernel(LoopGeom g, VoteArgs a, int first_loops, int entries_per_cta)
     for (int i = threadIdx.x; i < L * words; i += kVoteThreads) vote_bm[i] = gbm[i];
   if (threadIdx.x < kVoteMaxLoops)
     s_a[threadIdx.x] = threadIdx.x < L ? (unsigned)a.perm[(long long)s * perm_stride(g.loops) + threadIdx.x] : 0u;
+  if (threadIdx.x == 0) s_nhit = 0;
   __syncthreads();
   const unsigned *bm = SMEM_MAPS ? vote_bm : gbm;
   unsigned ai[kVoteMaxLoops];
@@ -927,9 +933,22 @@ vote_kernel(LoopGeom g, VoteArgs a, int first_loops, int entries_per_cta)
       }
     }
     if (!earlier && score >= a.thresh) {
-      const int pos = atomicAdd(&a.count[s], 1);
-      if (pos < a.hits_cap) a.hits[(long long)s * a.hits_cap + pos] = (int)loc;
+      const int slot = atomicAdd(&s_nhit, 1);
+      if (slot < kVoteHitCap) {
+        s_hits[slot] = (int)loc;
+      } else {
+        const int pos = atomicAdd(&a.count[s], 1);
+        if (pos < a.hits_cap) a.hits[(long long)s * a.hits_cap + pos] = (int)loc;
+      }
     }
+  }
+  __syncthreads();
+  const int mine = s_nhit < kVoteHitCap ? s_nhit : kVoteHitCap;
+  if (threadIdx.x == 0 && mine > 0) s_base = atomicAdd(&a.count[s], mine);
+  __syncthreads();
+  for (int i = threadIdx.x; i < mine; i += kVoteThreads) {
+    const int pos = s_base + i;
+    if (pos < a.hits_cap) a.hits[(long long)s * a.hits_cap + pos] = s_hits[i];
   }
 }
 
@@ -985,15 +1004,18 @@ int launch_vote(const LoopGeom &g, const VoteArgs &a, int nsig, cudaStream_t st)
     if (blocks > cap) blocks = cap;
     vote_generic_kernel<<<dim3((unsigned)blocks, (unsigned)nsig), kVoteThreads, 0, st>>>(g, a, first_loops);
   } else {
-    // ~32 candidates per thread: 8192 candidates = 8192 / (n/B) entries per CTA
+    // voting is latency-bound per CTA: as many CTAs as there are entries, until the grid is a
+    // few waves deep; beyond that (batches) a CTA takes up to 4096 candidates' worth of entries
     const int logseg = g.logn - g.logB[0];
-    int per_cta = logseg >= 13 ? 1 : (8192 >> logseg);
-    if (per_cta > entries) per_cta = (int)entries;
+    long long per_cta = entries * nsig / 600;
+    const long long most = logseg >= 12 ? 1 : (4096 >> logseg);
+    if (per_cta > most) per_cta = most;
+    if (per_cta < 1) per_cta = 1;
     const long long blocks = (entries + per_cta - 1) / per_cta;
     const dim3 grid((unsigned)blocks, (unsigned)nsig);
     const size_t smem = sizeof(unsigned) * (size_t)g.loops_loc * words;
-    if (smem <= 48 * 1024) vote_kernel<true><<<grid, kVoteThreads, smem, st>>>(g, a, first_loops, per_cta);
-    else vote_kernel<false><<<grid, kVoteThreads, 0, st>>>(g, a, first_loops, per_cta);
+    if (smem <= 48 * 1024) vote_kernel<true><<<grid, kVoteThreads, smem, st>>>(g, a, first_loops, (int)per_cta);
+    else vote_kernel<false><<<grid, kVoteThreads, 0, st>>>(g, a, first_loops, (int)per_cta);
   }
   SFFTB_LAUNCH_CHECK();
   return 0;

@@ -521,6 +521,7 @@ __device__ void mansour_targets(const PeelCtx &c, int key, cplx value, int *slot
 // Deterministic whatever the thread timing: targets are grouped by bucket (atomics decide
 // only where a bucket's segment sits and the order INSIDE it), then one thread per touched
 // bucket applies its segment in ascending target id, i.e. in item order.  Four team phases.
+constexpr int kPeelSegLocal = 64;       // peel_apply: segments up to this long are applied out of local memory
 constexpr int kSmallTargets = 1024;     // peel_apply: up to this many targets are handled by CTA 0 in shared memory
 struct PeelSmall {
   int slot[kSmallTargets];
@@ -591,36 +592,34 @@ __device__ void peel_apply(const PeelCtx &c, Team &tm, const int *keys, const cp
   int *touched = c.t_next + g.nslots;             // [nslots] buckets with at least one target
   int *seg = c.t_next + 2 * g.nslots;             // [F*14] target ids grouped by bucket
   int *ntouched = tm.ctr + 0, *seg_alloc = tm.ctr + 1;   // zero between calls
-  for (int i = tm.tid; i < F; i += tm.nthreads) {
-    const int key = keys[i];
-    const cplx v = vals[i];
-    int slots[14];
-    cplx deltas[14];
+  // one thread per (item, filter): the trigonometry of the three filters runs side by side
+  for (int u = tm.tid; u < 3 * F; u += tm.nthreads) {
+    const int i = u / 3, part = u - 3 * i;
+    const bool on = part == 0 ? do_g2 : (part == 1 ? do_g1 : do_man);
+    const int cntp = part == 2 ? 2 : 6;
+    int slots[6];
+    cplx deltas[6];
+    item_targets(c, part, keys[i], vals[i], on, slots, deltas);
+    // all counters at once (one round trip), then one slot reservation for the buckets
+    // this thread touched first
+    int old[6], nfirst = 0;
+    const int tbase = i * 14 + part * 6;
 #pragma unroll
-    for (int q = 0; q < 14; q++) slots[q] = -1;
-    if (do_g2) {
-      const int key2 = (int)(((((unsigned long long)(unsigned)key * (unsigned)c.ai) & (unsigned)(g.n - 1)) +
-                              (unsigned)c.shift) % (unsigned)g.n);
-      const int a_off = (int)((unsigned)c.a * (unsigned)c.goff);
-      gauss_targets(c, 2, key2, v, a_off, slots, deltas);
-    }
-    if (do_g1) gauss_targets(c, 1, key, v, c.goff, slots + 6, deltas + 6);
-    if (do_man) mansour_targets(c, key, v, slots + 12, deltas + 12);
-    // all 14 counters at once (one round trip), then one slot reservation for the buckets
-    // this item touched first
-    int old[14], nfirst = 0;
-#pragma unroll
-    for (int q = 0; q < 14; q++) {
-      const int t = i * 14 + q;
-      c.t_slot[t] = slots[q];
-      if (slots[q] >= 0) c.t_delta[t] = deltas[q];
-      old[q] = slots[q] >= 0 ? atomicAdd(&cnt[slots[q]], 1) : 1;
+    for (int q = 0; q < 6; q++) {
+      old[q] = 1;
+      if (q < cntp) {
+        c.t_slot[tbase + q] = slots[q];
+        if (slots[q] >= 0) {
+          c.t_delta[tbase + q] = deltas[q];
+          old[q] = atomicAdd(&cnt[slots[q]], 1);
+        }
+      }
     }
 #pragma unroll
-    for (int q = 0; q < 14; q++) nfirst += old[q] == 0;
+    for (int q = 0; q < 6; q++) nfirst += old[q] == 0;
     int tpos = nfirst ? atomicAdd(ntouched, nfirst) : 0;
 #pragma unroll
-    for (int q = 0; q < 14; q++)
+    for (int q = 0; q < 6; q++)
       if (old[q] == 0) touched[tpos++] = slots[q];
   }
   tm.sync();
@@ -642,14 +641,32 @@ __device__ void peel_apply(const PeelCtx &c, Team &tm, const int *keys, const cp
     const int *ids = seg + (fill[sl] - len);
     cplx val = c.samp[sl];
     int last = -1;
-    for (int rep = 0; rep < len; rep++) {          // ascending target id == item order
-      int best = 0x7fffffff;
-      for (int q = 0; q < len; q++) {
-        const int id = ids[q];
-        if (id > last && id < best) best = id;
+    if (len <= kPeelSegLocal) {
+      // fetch the segment's deltas with independent loads first: the ordered subtraction then
+      // runs out of local memory instead of paying an L2 round trip per delta
+      int idl[kPeelSegLocal];
+      cplx dl[kPeelSegLocal];
+      for (int q = 0; q < len; q++) idl[q] = ids[q];
+      for (int q = 0; q < len; q++) dl[q] = c.t_delta[idl[q]];
+      for (int rep = 0; rep < len; rep++) {          // ascending target id == item order
+        int best = 0x7fffffff, bq = 0;
+        for (int q = 0; q < len; q++) {
+          const int id = idl[q];
+          if (id > last && id < best) { best = id; bq = q; }
+        }
+        val = csub_rn(val, dl[bq]);
+        last = best;
       }
-      val = csub_rn(val, c.t_delta[best]);
-      last = best;
+    } else {
+      for (int rep = 0; rep < len; rep++) {
+        int best = 0x7fffffff;
+        for (int q = 0; q < len; q++) {
+          const int id = ids[q];
+          if (id > last && id < best) best = id;
+        }
+        val = csub_rn(val, c.t_delta[best]);
+        last = best;
+      }
     }
     c.samp[sl] = val;
     cnt[sl] = 0;

@@ -89,6 +89,23 @@ def test_device_built_filters_agree_with_the_oracle(oracle_mod, version, n, k):
     op.free()
 
 
+@pytest.mark.parametrize("n,k", [(16384, 50), (1 << 18, 100), (1 << 22, 50)])
+def test_host_thread_chains_of_the_plan_builder(oracle_mod, monkeypatch, n, k):
+    """For n >= 2^24 the plan builder runs its two history-dependent recurrences (boxcar running
+    sum, phase-ramp running product: src/filters.cc:119-140) on host threads instead of
+    single GPU threads.  Forced on at sizes the oracle builds in seconds: same bits."""
+    monkeypatch.setenv("SFFTB_HOST_CHAINS", "1")
+    p = make_plan(n, k, 1)
+    monkeypatch.delenv("SFFTB_HOST_CHAINS")
+    op = oracle_mod.Plan(n, k, 1)
+    for which, (t, f, B) in enumerate((("time_loc", "freq_loc", op.B_loc), ("time_est", "freq_est", op.B_est))):
+        gt, gf = p.get_filter(which)
+        assert bits_equal(gt, op.arr(t)), np.abs(gt - op.arr(t)).max()
+        assert bits_equal(gf, fwin_from_full(op.arr(f), (op.n // B) // 2))
+    p.close()
+    op.free()
+
+
 @pytest.mark.parametrize("version,n,k", CASES)
 def test_every_stage_bit_identical_with_injected_filters(oracle_mod, version, n, k):
     x, xf = oracle_mod.generate_input(n, k, 4242)
