@@ -6,8 +6,7 @@ import ctypes as C
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-# SFFTB_LIB selects an experiment build of the same library (sfft_b200/build.py VARIANT)
-LIB_PATH = os.environ.get("SFFTB_LIB") or os.path.join(HERE, "libsfft.so")
+LIB_PATH = os.path.join(HERE, "libsfft.so")
 
 SFFTB_MAX_LOOPS = 64
 SFFTB_MAX_COMB_LOOPS = 16

@@ -11,11 +11,8 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-# experiment builds: SFFTB_BUILD_VARIANT=t8 -> libsfft_t8.so with -DSFFTB_V2_LOG_TILE=8 (loaded via SFFTB_LIB)
-VARIANT = os.environ.get("SFFTB_BUILD_VARIANT", "")
-VARIANT_FLAGS = {"": [], "t8": ["-DSFFTB_V2_LOG_TILE=8"]}[VARIANT]
-OUT = os.path.join(HERE, "libsfft%s.so" % ("_" + VARIANT if VARIANT else ""))
-BUILD = os.path.join(HERE, "build" + ("_" + VARIANT if VARIANT else ""))
+OUT = os.path.join(HERE, "libsfft.so")
+BUILD = os.path.join(HERE, "build")
 
 CU_SOURCES = ["api.cu", "fft.cu", "plan_builder.cu", "plan_v12.cu", "v12_kernels.cu", "v3.cu", "shard.cu"]
 C_SOURCES = ["cheb_host.c"]
@@ -53,7 +50,7 @@ def build(force=False, verbose=False):
     procs = []
     for src in CU_SOURCES:
         obj = os.path.join(BUILD, src + ".o")
-        cmd = [NVCC] + NVCC_FLAGS + VARIANT_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+        cmd = [NVCC] + NVCC_FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd))
         procs.append((src, subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT)))
@@ -76,8 +73,7 @@ def build(force=False, verbose=False):
     link = [NVCC, "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-ccbin", HOST_CXX,
             "-o", OUT] + objs + ["-lm", "-lpthread"]
     subprocess.check_call(link)
-    if not VARIANT:
-        build_tools()
+    build_tools()
     return OUT
 
 
@@ -91,7 +87,7 @@ def build_tools():
         subprocess.check_call([HOST_CXX, "-O2", f"-DHARNESS_MODE={mode}", src, "-I", os.path.join(root, "include"),
                                "-L", HERE, "-lsfft", f"-Wl,-rpath,{HERE}", "-Wl,-rpath,$ORIGIN/../sfft_b200",
                                "-o", os.path.join(tools, name)])
-    for mb in ("random_gather", "ld_variants", "bulk_copy", "pipe_overlap"):
+    for mb in ("random_gather", "ld_variants", "bulk_copy", "pipe_overlap", "cluster_barrier"):
         cu = os.path.join(tools, "microbench", mb + ".cu")
         if os.path.exists(cu):
             subprocess.check_call([NVCC, "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo",

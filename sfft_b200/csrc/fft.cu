@@ -62,7 +62,9 @@ void host_twiddle_factors(long n, std::vector<cplx> &coarse, std::vector<cplx> &
 // ---------------------------------------------------------------------------
 constexpr int kFftThreads = 256;
 constexpr int kTwFineLog = 14;         // == log2(ORC_TW_FINE) of the oracle's definition
-constexpr int kMaxTileLog = 11;        // 2048 points = 32 KB of shared memory
+constexpr int kMaxTileLog = 11;        // 2048 points = 32 KB of shared memory.  (Round 2 tried ONE 8192-point
+                                       // pass for C1's location rows -- 144 KB tile, twiddles from L1/L2, three
+                                       // CTAs of work -- and measured it slower than this plus a second pass: 55 vs 28 us.)
 constexpr int kLaterPassStages = 8;    // keeps >= 8 adjacent columns (128 B) per row
 
 // TABLE: `tw` is the level-ordered twiddle table (host_twiddle_levels).  The first

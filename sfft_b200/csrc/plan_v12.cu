@@ -262,7 +262,7 @@ int v12_ensure_capacity(PlanImpl *p, int nsig)
     if (v2_struct_supported(v.geom, ilog2((unsigned)W)) && !getenv("SFFTB_NO_V2_STRUCT")) {
       SFFTB_CUDA(cudaMalloc(&v.d_xt, sizeof(cplx) * S * v.x_samp_size));
       SFFTB_CUDA(cudaMalloc(&v.d_run_unsafe, (size_t)(S * v.x_samp_size) >> v2_struct_log_tile(v.geom, ilog2((unsigned)W))));
-      SFFTB_CUDA(cudaMalloc(&v.d_tile_counter, sizeof(unsigned) * (S + 256)));
+      SFFTB_CUDA(cudaMalloc(&v.d_tile_counter, sizeof(unsigned) * S));
     }
   }
   v.gkeys_per_sig = gk;
@@ -515,7 +515,6 @@ static int v12_stage_finish(PlanImpl *p, int nsig, int slice_rank, int slice_wor
     sa2.logW = ilog2((unsigned)v.W_Comb);
     sa2.logT = v2_struct_log_tile(g, sa2.logW);
     sa2.out_loc = v.d_hit_loc; sa2.out_val = v.d_hit_val; sa2.out_cap = v.max_hits;
-    sa2.skew_cycles = 0;
     sa2.slice_rank = ea.slice_rank; sa2.slice_world = ea.slice_world; sa2.slice_count = ea.slice_count;
     if (launch_v2_struct(g, sa2, v.max_comb, nsig, st)) return -1;
   } else {

@@ -867,18 +867,23 @@ int launch_select(const SelectArgs &a, int nrows, int nsig, cudaStream_t st)
 // a flat index were most of the old kernel's instructions.
 constexpr int kVoteThreads = 256;
 constexpr int kVoteMaxLoops = 8;        // location loops kept in registers; more -> generic path
+constexpr int kVoteMaxEntries = 16;     // selected buckets one CTA may own
 constexpr int kVoteHitCap = 2048;       // hits a CTA collects in shared memory before it falls back to global atomics
 
-template <bool SMEM_MAPS>
+// AGGREGATE: collect the CTA's hits in shared memory and append them with one global atomic
+// (batches: thousands of atomics on one signal's counter serialise in L2); a single signal's
+// short CTAs are better off with direct atomics.
+template <bool SMEM_MAPS, bool AGGREGATE>
 __global__ void __launch_bounds__(kVoteThreads)
 vote_kernel(LoopGeom g, VoteArgs a, int first_loops, int entries_per_cta)
 {
   extern __shared__ unsigned vote_bm[];          // [loops_loc][words] when SMEM_MAPS
-  __shared__ unsigned s_a[kVoteMaxLoops];        // a_j of the candidate-generating loops
   // hits of this CTA, appended to the global list with ONE atomic: thousands of atomics on one
   // signal's counter serialise in L2 (~3 ns each), which was most of a batch's voting time
-  __shared__ int s_hits[kVoteHitCap];
+  __shared__ int s_hits[AGGREGATE ? kVoteHitCap : 1];
   __shared__ int s_nhit, s_base;
+  __shared__ unsigned s_low[kVoteMaxEntries];    // first permuted position of each entry's bucket
+  __shared__ unsigned s_aj[kVoteMaxEntries];     // a_j of the entry's loop
   const int s = blockIdx.y;
   const int logB = g.logB[0];
   const int logseg = g.logn - logB;
@@ -889,8 +894,17 @@ vote_kernel(LoopGeom g, VoteArgs a, int first_loops, int entries_per_cta)
   const unsigned *gbm = a.bitmap + (long long)s * a.bm_sig_stride;
   if (SMEM_MAPS)
     for (int i = threadIdx.x; i < L * words; i += kVoteThreads) vote_bm[i] = gbm[i];
-  if (threadIdx.x < kVoteMaxLoops)
-    s_a[threadIdx.x] = threadIdx.x < L ? (unsigned)a.perm[(long long)s * perm_stride(g.loops) + threadIdx.x] : 0u;
+  const int total_entries = first_loops * a.num;
+  const int e0 = blockIdx.x * entries_per_cta;
+  const int e1 = e0 + entries_per_cta < total_entries ? e0 + entries_per_cta : total_entries;
+  if ((int)threadIdx.x < e1 - e0) {
+    // J is [loops_loc][num]; entry e of the flattened list is J[j][e - j*num], i.e. J[e]
+    const int e = e0 + (int)threadIdx.x;
+    const unsigned Jv = (unsigned)a.J[(long long)s * a.J_sig_stride + e];
+    // cf12.cc:102: low = ceil((J - 0.5) * n/B) mod n  == J*seg - seg/2 (exact for seg >= 2)
+    s_low[threadIdx.x] = ((Jv << logseg) - half) & mask;
+    s_aj[threadIdx.x] = (unsigned)a.perm[(long long)s * perm_stride(g.loops) + e / a.num];
+  }
   if (threadIdx.x == 0) s_nhit = 0;
   __syncthreads();
   const unsigned *bm = SMEM_MAPS ? vote_bm : gbm;
@@ -901,23 +915,15 @@ vote_kernel(LoopGeom g, VoteArgs a, int first_loops, int entries_per_cta)
   const unsigned *cb = a.comb_bitmap ? a.comb_bitmap + (long long)s * a.comb_sig_stride : nullptr;
 
   // this CTA's (loop, entry) pairs, flattened with their n/B positions: every thread walks
-  // candidates of several entries, so the entries' dependent loads overlap
-  const int total_entries = first_loops * a.num;
-  const int e0 = blockIdx.x * entries_per_cta;
-  const int e1 = e0 + entries_per_cta < total_entries ? e0 + entries_per_cta : total_entries;
+  // candidates of several entries, whose constants were fetched side by side above
   const unsigned ncand = (unsigned)(e1 - e0) << logseg;
-  const int *Jrow = a.J + (long long)s * a.J_sig_stride;
   int j = e0 / a.num;                              // loops of consecutive entries only ever increase
   for (unsigned c = threadIdx.x; c < ncand; c += kVoteThreads) {
-    const int e = e0 + (int)(c >> logseg);
+    const int le = (int)(c >> logseg);
     const unsigned t = c & (seg - 1u);
-    while (e >= (j + 1) * a.num) j++;
-    // J is [loops_loc][num]; entry e of the flattened list is J[j][e - j*num], i.e. J[e]
-    const unsigned Jv = (unsigned)__ldg(&Jrow[e]);
-    // cf12.cc:102: low = ceil((J - 0.5) * n/B) mod n  == J*seg - seg/2 (exact for seg >= 2)
-    const unsigned low = ((Jv << logseg) - half) & mask;
-    const unsigned p = (low + t) & mask;
-    const unsigned loc = (s_a[j] * p) & mask;                     // n is a power of two <= 2^31
+    while (e0 + le >= (j + 1) * a.num) j++;
+    const unsigned p = (s_low[le] + t) & mask;
+    const unsigned loc = (s_aj[le] * p) & mask;                   // n is a power of two <= 2^31
     const unsigned rres = loc & (unsigned)a.W_mask;              // v2: loc mod W_Comb must be approved
     if (cb && !((__ldg(&cb[rres >> 5]) >> (rres & 31u)) & 1u)) continue;
     // emitted by the first loop that votes for it; score = votes over all location loops
@@ -933,7 +939,7 @@ vote_kernel(LoopGeom g, VoteArgs a, int first_loops, int entries_per_cta)
       }
     }
     if (!earlier && score >= a.thresh) {
-      const int slot = atomicAdd(&s_nhit, 1);
+      const int slot = AGGREGATE ? atomicAdd(&s_nhit, 1) : kVoteHitCap;
       if (slot < kVoteHitCap) {
         s_hits[slot] = (int)loc;
       } else {
@@ -942,6 +948,7 @@ vote_kernel(LoopGeom g, VoteArgs a, int first_loops, int entries_per_cta)
       }
     }
   }
+  if (!AGGREGATE) return;
   __syncthreads();
   const int mine = s_nhit < kVoteHitCap ? s_nhit : kVoteHitCap;
   if (threadIdx.x == 0 && mine > 0) s_base = atomicAdd(&a.count[s], mine);
@@ -1008,14 +1015,18 @@ int launch_vote(const LoopGeom &g, const VoteArgs &a, int nsig, cudaStream_t st)
     // few waves deep; beyond that (batches) a CTA takes up to 4096 candidates' worth of entries
     const int logseg = g.logn - g.logB[0];
     long long per_cta = entries * nsig / 600;
-    const long long most = logseg >= 12 ? 1 : (4096 >> logseg);
+    long long most = logseg >= 12 ? 1 : (4096 >> logseg);
+    if (most > kVoteMaxEntries) most = kVoteMaxEntries;
     if (per_cta > most) per_cta = most;
     if (per_cta < 1) per_cta = 1;
     const long long blocks = (entries + per_cta - 1) / per_cta;
     const dim3 grid((unsigned)blocks, (unsigned)nsig);
     const size_t smem = sizeof(unsigned) * (size_t)g.loops_loc * words;
-    if (smem <= 48 * 1024) vote_kernel<true><<<grid, kVoteThreads, smem, st>>>(g, a, first_loops, (int)per_cta);
-    else vote_kernel<false><<<grid, kVoteThreads, 0, st>>>(g, a, first_loops, (int)per_cta);
+    const bool maps = smem <= 32 * 1024, agg = nsig > 1;
+    if (maps && agg) vote_kernel<true, true><<<grid, kVoteThreads, smem, st>>>(g, a, first_loops, (int)per_cta);
+    else if (maps) vote_kernel<true, false><<<grid, kVoteThreads, smem, st>>>(g, a, first_loops, (int)per_cta);
+    else if (agg) vote_kernel<false, true><<<grid, kVoteThreads, 0, st>>>(g, a, first_loops, (int)per_cta);
+    else vote_kernel<false, false><<<grid, kVoteThreads, 0, st>>>(g, a, first_loops, (int)per_cta);
   }
   SFFTB_LAUNCH_CHECK();
   return 0;
@@ -1298,10 +1309,10 @@ int launch_estimate(const LoopGeom &g, const EstimateArgs &a, int nsig, long lon
 // ---------------------------------------------------------------------------
 // v2 structured estimation (see v12_kernels.cuh)
 // ---------------------------------------------------------------------------
-#ifndef SFFTB_V2_LOG_TILE
-#define SFFTB_V2_LOG_TILE 9
-#endif
-constexpr int kV2LogTile = SFFTB_V2_LOG_TILE;   // hits per tile = threads per CTA (512: one CTA per SM, 8 KB runs)
+// hits per tile = threads per CTA: one CTA per SM, 8 KB runs.  256-hit tiles with two CTAs per SM
+// are slower (0.965 vs 0.955 ms at C2), also when the second CTA starts half a tile period late
+// so that the two sit in opposite phases (profiles/r02_v2_tile256_skew.jsonl).
+constexpr int kV2LogTile = 9;
 constexpr int kV2MaxSmem = 227 * 1024 - 8192;   // dynamic shared memory a CTA may ask for (static: parameters)
 
 __device__ __forceinline__ void v2_slice(const V2StructArgs &a, long long total, long long &lo, long long &hi)
@@ -1328,8 +1339,6 @@ v2_regroup_kernel(LoopGeom g, const cplx *__restrict__ xs, cplx *__restrict__ xt
   const int logB = j >= g.loops_loc ? g.logB[1] : g.logB[0];
   const int t = logB - logT;
   if (blockIdx.x == 0 && j == 0 && threadIdx.x == 0) tile_counter[blockIdx.z] = 0u;
-  // per-SM arrival counters of the estimation kernel's start-up skew (behind the tile counters)
-  if (blockIdx.x == 0 && j == 0 && blockIdx.z == 0 && threadIdx.x < 256) tile_counter[gridDim.z + threadIdx.x] = 0u;
   const unsigned o = blockIdx.x * blockDim.x + threadIdx.x;
   if (o >= (1u << logB)) return;
   const unsigned b = (o >> logT) | ((o & ((1u << logT) - 1u)) << t);
@@ -1455,16 +1464,6 @@ v2_fused_kernel(LoopGeom g, V2StructArgs a)
     mbar_init(full, L);
     mbar_init(empty, T / 32);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    if (a.skew_cycles > 0) {
-      // two CTAs share an SM (T = 256): the second to arrive starts half a tile period late, so
-      // that one CTA's FP64-heavy divisions run under the other's ALU-heavy medians
-      unsigned smid;
-      asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
-      if (atomicAdd(a.tile_counter + gridDim.y + (smid & 255u), 1u) & 1u) {
-        const long long t0 = clock64();
-        while (clock64() - t0 < a.skew_cycles) {}
-      }
-    }
     prm.chunk = atomicAdd(ctr, 1u);
   }
   __syncthreads();
@@ -1619,13 +1618,6 @@ int launch_v2_struct(const LoopGeom &g, const V2StructArgs &a, int max_comb, int
   constexpr int logT = kV2LogTile, T = 1 << logT;
   const int maxlog = g.logB[0] > g.logB[1] ? g.logB[0] : g.logB[1];
   dim3 rgrid(1u << (maxlog - logT), (unsigned)g.loops, (unsigned)nsig);
-  V2StructArgs aa = a;
-  static int skew = -1;
-  if (skew < 0) {
-    const char *e = getenv("SFFTB_V2_SKEW");
-    skew = e ? atoi(e) : 0;
-  }
-  aa.skew_cycles = (512 >> kV2LogTile) > 1 ? skew : 0;
   v2_regroup_kernel<<<rgrid, T, 0, st>>>(g, a.xs, a.xt, a.run_unsafe, a.tile_counter);
   SFFTB_LAUNCH_CHECK();
   const size_t flag_bytes = ((size_t)(g.x_samp_size >> logT) + 15) & ~(size_t)15;
@@ -1641,7 +1633,7 @@ int launch_v2_struct(const LoopGeom &g, const V2StructArgs &a, int max_comb, int
   case N: {                                                                                       \
     SFFTB_ONCE_PER_DEVICE(SFFTB_CUDA(cudaFuncSetAttribute(                                        \
         v2_fused_kernel<N>, cudaFuncAttributeMaxDynamicSharedMemorySize, kV2MaxSmem)));           \
-    v2_fused_kernel<N><<<grid, T, smem, st>>>(g, aa);                                             \
+    v2_fused_kernel<N><<<grid, T, smem, st>>>(g, a);                                              \
   } break;
     SFFTB_V2F_CASE(2) SFFTB_V2F_CASE(3) SFFTB_V2F_CASE(4) SFFTB_V2F_CASE(5) SFFTB_V2F_CASE(6)
     SFFTB_V2F_CASE(7) SFFTB_V2F_CASE(8) SFFTB_V2F_CASE(9) SFFTB_V2F_CASE(10) SFFTB_V2F_CASE(11)

@@ -94,8 +94,7 @@ struct V2StructArgs {
   const cplx *xs;                  // bucket spectra            [nsig][x_samp_size]
   cplx *xt;                        // class-major copy of them   [nsig][x_samp_size]
   unsigned char *run_unsafe;       // per run of 2^logT elements of xt: needs real divisions
-  unsigned *tile_counter;          // [nsig] dynamic tile scheduler, then [256] per-SM arrival counters
-  int skew_cycles;                 // start-up skew of the second CTA of an SM (0: none)
+  unsigned *tile_counter;          // [nsig] dynamic tile scheduler
   const cplx *fwin[2]; int fw_half[2]; const double2 *fdr[2];
   const int *approved; long long approved_stride; const int *num_comb;
   int logW;                        // W_Comb = 2^logW

@@ -515,6 +515,26 @@ __device__ void mansour_targets(const PeelCtx &c, int key, cplx value, int *slot
   deltas[1] = make_double2(W * (value.x * c1 - value.y * s1), W * (value.x * s1 + value.y * c1));
 }
 
+// Reserve `want` consecutive units of *counter for every lane of the (converged) calling warp with
+// ONE atomic: returns this lane's first unit.
+__device__ __forceinline__ int warp_reserve(int *counter, int want)
+{
+  const unsigned active = __activemask();
+  const int lane = threadIdx.x & 31;
+  int incl = want;
+#pragma unroll
+  for (int off = 1; off < 32; off <<= 1) {
+    const int v = __shfl_up_sync(active, incl, off);
+    if (lane >= off) incl += v;
+  }
+  const int last = 31 - __clz(active);
+  const int total = __shfl_sync(active, incl, last);
+  int base = 0;
+  if (lane == last && total > 0) base = atomicAdd(counter, total);
+  base = __shfl_sync(active, base, last);
+  return base + incl - want;
+}
+
 // Subtract, from every touched bucket, the deltas of items [0, F) in item order.
 // keys/vals: the items (plain frequencies; the permuted filter sees (key*ai + shift) mod n,
 // :465-482, :944); the flags say which filters to peel.
@@ -559,8 +579,7 @@ __device__ void peel_apply(const PeelCtx &c, Team &tm, const int *keys, const cp
     // memory, one thread per (item, filter) for the trigonometry, then one thread per touched
     // bucket subtracts that bucket's deltas in ascending target id = item order
     if (tm.rank == 0) {
-      const int u = threadIdx.x;
-      if (u < 3 * F) {
+      for (int u = threadIdx.x; u < 3 * F; u += kPeelThreads) {
         const int i = u / 3, part = u - 3 * i;
         const bool on = part == 0 ? do_g2 : (part == 1 ? do_g1 : do_man);
         int sl[6];
@@ -572,7 +591,7 @@ __device__ void peel_apply(const PeelCtx &c, Team &tm, const int *keys, const cp
       }
       __syncthreads();
       const int T = F * 14;
-      if (u < T) {
+      for (int u = threadIdx.x; u < T; u += kPeelThreads) {
         const int slot = sm.slot[u];
         bool first = slot >= 0;
         for (int t = 0; first && t < u; t++) first = sm.slot[t] != slot;
@@ -617,7 +636,7 @@ __device__ void peel_apply(const PeelCtx &c, Team &tm, const int *keys, const cp
     }
 #pragma unroll
     for (int q = 0; q < 6; q++) nfirst += old[q] == 0;
-    int tpos = nfirst ? atomicAdd(ntouched, nfirst) : 0;
+    int tpos = warp_reserve(ntouched, nfirst);        // one atomic per warp: same-address atomics serialise in L2
 #pragma unroll
     for (int q = 0; q < 6; q++)
       if (old[q] == 0) touched[tpos++] = slots[q];
@@ -625,9 +644,11 @@ __device__ void peel_apply(const PeelCtx &c, Team &tm, const int *keys, const cp
   tm.sync();
   const int T = __ldcg(ntouched);
   // a segment per touched bucket; where it sits does not matter
-  for (int j = tm.tid; j < T; j += tm.nthreads) {
-    const int sl = touched[j];
-    fill[sl] = atomicAdd(seg_alloc, cnt[sl]);
+  for (int j0 = 0; j0 < T; j0 += tm.nthreads) {      // whole warps stay together for the reservation
+    const int j = j0 + tm.tid;
+    const int sl = j < T ? touched[j] : -1;
+    const int base = warp_reserve(seg_alloc, sl >= 0 ? cnt[sl] : 0);
+    if (sl >= 0) fill[sl] = base;
   }
   tm.sync();
   for (int t = tm.tid; t < F * 14; t += tm.nthreads) {

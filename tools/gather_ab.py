@@ -48,7 +48,7 @@ def main():
             for nm, ms in plan.stage_times().items():
                 acc.setdefault(nm, []).append(ms)
     samples = batch * (info["gather_samples"] - (info["Comb_loops"] * info["W_Comb"] if version == 2 else 0))
-    extra = {k: os.environ[k] for k in ("SFFTB_V2_SKEW", "SFFTB_LIB", "SFFTB_GATHER_UNROLL", "SFFTB_V3_TEAM") if k in os.environ}
+    extra = {k: os.environ[k] for k in ("SFFTB_GATHER_UNROLL", "SFFTB_V3_TEAM", "SFFTB_HOST_CHAINS", "SFFTB_NO_SELECT_CLUSTER") if k in os.environ}
     g = sum(acc["gather"]) / len(acc["gather"]) if "gather" in acc else None
     out = {"workload": wl, "fill": os.environ.get("SFFTB_GATHER_FILL", "auto"),
            "l2_fetch": os.environ.get("SFFTB_L2_FETCH", "default"), "gather_ms": g, "samples": samples,
