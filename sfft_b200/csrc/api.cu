@@ -17,7 +17,7 @@
 namespace sfftb {
 
 static thread_local std::string t_error;
-long long g_launches = 0;
+std::atomic<long long> g_launches{0};
 
 void set_error(const std::string &msg)
 {
@@ -72,7 +72,7 @@ int sfftb_device_count(void)
   return c;
 }
 
-long long sfftb_launch_count(void) { return g_launches; }
+long long sfftb_launch_count(void) { return g_launches.load(); }
 
 /* ------------------------------------------------------------------------ */
 /* Part 1: drop-in boundary                                                  */
@@ -606,8 +606,11 @@ int sfftb_debug_fft(const sfft_complex *in, sfft_complex *out, int log2n, int ba
   if (sfftb_device_count() <= 0) { set_error("sfftb_debug_fft: no CUDA device"); return -1; }
   const long long n = 1ll << log2n, total = n * batch;
   cplx *d_a = nullptr, *d_b = nullptr, *d_tw = nullptr;
+  ScratchGuard guard;
   SFFTB_CUDA(cudaMalloc(&d_a, sizeof(cplx) * total));
+  guard.track(d_a);
   SFFTB_CUDA(cudaMalloc(&d_b, sizeof(cplx) * total));
+  guard.track(d_b);
   SFFTB_CUDA(cudaMemcpy(d_a, in, sizeof(cplx) * total, cudaMemcpyHostToDevice));
   for (int b = 0; b < batch; b++)
     if (bitrev_permute(d_a + b * n, d_b + b * n, log2n, 0)) return -1;
@@ -615,12 +618,14 @@ int sfftb_debug_fft(const sfft_complex *in, sfft_complex *out, int log2n, int ba
     std::vector<cplx> tw((size_t)(n > 1 ? n - 1 : 1));
     host_twiddle_levels(n, tw.data());
     SFFTB_CUDA(cudaMalloc(&d_tw, sizeof(cplx) * tw.size()));
+    guard.track(d_tw);
     SFFTB_CUDA(cudaMemcpy(d_tw, tw.data(), sizeof(cplx) * tw.size(), cudaMemcpyHostToDevice));
   }
   if (fft_dit_inplace(d_b, log2n, batch, n, 1, total, d_tw, log2n, sign, 0)) return -1;
   SFFTB_CUDA(cudaDeviceSynchronize());
   SFFTB_CUDA(cudaMemcpy(out, d_b, sizeof(cplx) * total, cudaMemcpyDeviceToHost));
   cudaFree(d_a); cudaFree(d_b); cudaFree(d_tw);
+  guard.dismiss();
   return 0;
 }
 
@@ -637,10 +642,17 @@ int sfftb_debug_select(const double *mags, int B, int num, int batch, int *out_J
   for (long long i = 0; i < total; i++) h[(size_t)i] = make_double2(mags[i], 0.0);
   cplx *d_x = nullptr; int *d_J = nullptr; unsigned *d_bm = nullptr; unsigned long long *d_k = nullptr;
   const int words = B >= 32 ? B / 32 : 1;
+  ScratchGuard guard;
   SFFTB_CUDA(cudaMalloc(&d_x, sizeof(cplx) * total));
+  guard.track(d_x);
   SFFTB_CUDA(cudaMalloc(&d_J, sizeof(int) * (long long)num * batch));
+  guard.track(d_J);
   SFFTB_CUDA(cudaMalloc(&d_bm, sizeof(unsigned) * (long long)words * batch));
-  if (B > 16384) SFFTB_CUDA(cudaMalloc(&d_k, sizeof(unsigned long long) * select_gkeys_per_row(B) * batch));
+  guard.track(d_bm);
+  if (B > 16384) {
+    SFFTB_CUDA(cudaMalloc(&d_k, sizeof(unsigned long long) * select_gkeys_per_row(B) * batch));
+    guard.track(d_k);
+  }
   SFFTB_CUDA(cudaMemcpy(d_x, h.data(), sizeof(cplx) * total, cudaMemcpyHostToDevice));
   SelectArgs sa;
   sa.xs = d_x; sa.xs_stride = 0; sa.row_stride = B; sa.logB = ilog2((unsigned)B); sa.num = num;
@@ -650,6 +662,7 @@ int sfftb_debug_select(const double *mags, int B, int num, int batch, int *out_J
   SFFTB_CUDA(cudaDeviceSynchronize());
   SFFTB_CUDA(cudaMemcpy(out_J, d_J, sizeof(int) * (long long)num * batch, cudaMemcpyDeviceToHost));
   cudaFree(d_x); cudaFree(d_J); cudaFree(d_bm); cudaFree(d_k);
+  guard.dismiss();
   return 0;
 }
 
@@ -657,12 +670,16 @@ int sfftb_debug_dft_any(const sfft_complex *in, sfft_complex *out, int n)
 {
   if (sfftb_device_count() <= 0) { set_error("sfftb_debug_dft_any: no CUDA device"); return -1; }
   cplx *d_x = nullptr, *d_y = nullptr;
+  ScratchGuard guard;
   SFFTB_CUDA(cudaMalloc(&d_x, sizeof(cplx) * n));
+  guard.track(d_x);
   SFFTB_CUDA(cudaMalloc(&d_y, sizeof(cplx) * n));
+  guard.track(d_y);
   SFFTB_CUDA(cudaMemcpy(d_x, in, sizeof(cplx) * n, cudaMemcpyHostToDevice));
   if (bluestein_forward(d_x, n, d_y, 0)) return -1;
   SFFTB_CUDA(cudaMemcpy(out, d_y, sizeof(cplx) * n, cudaMemcpyDeviceToHost));
   cudaFree(d_x); cudaFree(d_y);
+  guard.dismiss();
   return 0;
 }
 

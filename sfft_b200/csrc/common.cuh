@@ -13,7 +13,7 @@ typedef double2 cplx;   // (x = re, y = im), 16-byte aligned -> LDG.E.128 / STG.
 
 // ---- error plumbing --------------------------------------------------------
 void set_error(const std::string &msg);
-extern long long g_launches;
+extern std::atomic<long long> g_launches;   // kernels launched by this library (any thread)
 
 #define SFFTB_CUDA(call)                                                            \
   do {                                                                              \
@@ -53,6 +53,27 @@ extern long long g_launches;
       done__.fetch_or(bit__, std::memory_order_release);                            \
     }                                                                               \
   } while (0)
+
+// Device temporaries of a host function that can return early: everything `track`ed is freed /
+// destroyed when the guard goes out of scope, unless the normal path (which frees in its own
+// order) has called dismiss().
+struct ScratchGuard {
+  void *dev[32];
+  cudaStream_t streams[8];
+  int ndev = 0, nstreams = 0;
+  bool armed = true;
+  template <class T> T *track(T *p) { if (p && ndev < 32) dev[ndev++] = (void *)p; return p; }
+  void track_stream(cudaStream_t s) { if (s && nstreams < 8) streams[nstreams++] = s; }
+  void forget(const void *p) { for (int i = 0; i < ndev; i++) if (dev[i] == p) dev[i] = nullptr; }
+  void dismiss() { armed = false; }
+  ~ScratchGuard()
+  {
+    if (!armed) return;
+    for (int i = 0; i < nstreams; i++) cudaStreamSynchronize(streams[i]);
+    for (int i = 0; i < ndev; i++) if (dev[i]) cudaFree(dev[i]);
+    for (int i = 0; i < nstreams; i++) cudaStreamDestroy(streams[i]);
+  }
+};
 
 // ---- exactly-rounded complex arithmetic ------------------------------------
 // The parity contract is "one IEEE rounding per product and per sum", the same

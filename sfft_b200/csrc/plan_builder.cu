@@ -468,10 +468,16 @@ int bluestein_forward(const cplx *d_x, int w, cplx *d_out, cudaStream_t st)
   Twiddles tw;
   if (make_twiddles(logM, &tw, st)) return -1;
   cplx *d_A = nullptr, *d_B = nullptr, *d_C = nullptr, *d_ch = nullptr;
+  ScratchGuard guard;
+  guard.track(tw.levels); guard.track(tw.coarse); guard.track(tw.fine);
   SFFTB_CUDA(cudaMalloc(&d_A, sizeof(cplx) * M));
+  guard.track(d_A);
   SFFTB_CUDA(cudaMalloc(&d_B, sizeof(cplx) * M));
+  guard.track(d_B);
   SFFTB_CUDA(cudaMalloc(&d_C, sizeof(cplx) * M));
+  guard.track(d_C);
   SFFTB_CUDA(cudaMalloc(&d_ch, sizeof(cplx) * w));
+  guard.track(d_ch);
   SFFTB_CUDA(cudaMemcpyAsync(d_ch, chirp.data(), sizeof(cplx) * w, cudaMemcpyHostToDevice, st));
   bluestein_prep_kernel<<<grid_for(M), kT, 0, st>>>(d_x, d_ch, w, logM, d_A, d_B);
   SFFTB_LAUNCH_CHECK();
@@ -485,6 +491,7 @@ int bluestein_forward(const cplx *d_x, int w, cplx *d_out, cudaStream_t st)
   SFFTB_CUDA(cudaStreamSynchronize(st));
   cudaFree(d_A); cudaFree(d_B); cudaFree(d_C); cudaFree(d_ch);
   free_twiddles(&tw);
+  guard.dismiss();
   return 0;
 }
 
@@ -519,9 +526,13 @@ int build_window(int logn, WindowWork *ww, const Twiddles &twn, cudaStream_t st)
 
   cplx *d_samples = nullptr, *d_X = nullptr;
   double *d_taps0 = nullptr;
+  ScratchGuard guard;
   SFFTB_CUDA(cudaMalloc(&d_samples, sizeof(cplx) * w));
+  guard.track(d_samples);
   SFFTB_CUDA(cudaMalloc(&d_X, sizeof(cplx) * w));
+  guard.track(d_X);
   SFFTB_CUDA(cudaMalloc(&d_taps0, sizeof(double) * w));
+  guard.track(d_taps0);
   SFFTB_CUDA(cudaMalloc(&ww->d_G, sizeof(cplx) * n));
   SFFTB_CUDA(cudaMalloc(&ww->d_R, sizeof(cplx) * n));
   // the phase ramp does not depend on the data: start its chain on its own stream now
@@ -547,6 +558,7 @@ int build_window(int logn, WindowWork *ww, const Twiddles &twn, cudaStream_t st)
   if (fft_with(twn, ww->d_G, -1, st)) return -1;
   SFFTB_CUDA(cudaStreamSynchronize(st));
   cudaFree(d_samples); cudaFree(d_X); cudaFree(d_taps0);
+  guard.dismiss();
   return 0;
 }
 
@@ -611,11 +623,28 @@ int build_filters(int logn, int count, const FilterSpec *specs, DeviceFilter **o
     which_win[f] = found;
   }
   StepClock clk;
+  // every device temporary below is registered here: an early `return -1` frees them (the
+  // filters' own arrays belong to the plan and are released by free_filter)
+  ScratchGuard guard;
+  // declared after the guard, hence destroyed before it: a host ramp chain still running on an
+  // early return is joined before its target buffer is freed
+  struct RampJoiner {
+    WindowWork *w;
+    ~RampJoiner()
+    {
+      for (int q = 0; q < 2; q++)
+        if (w[q].ramp_thread) { w[q].ramp_thread->join(); delete w[q].ramp_thread; w[q].ramp_thread = nullptr; }
+    }
+  } ramp_joiner{win};
   Twiddles twn;
   if (make_twiddles(logn, &twn, st)) return -1;
+  guard.track(twn.levels); guard.track(twn.coarse); guard.track(twn.fine);
   clk.mark("twiddles");
-  for (int q = 0; q < nwin; q++)
-    if (build_window(logn, &win[q], twn, st)) return -1;
+  for (int q = 0; q < nwin; q++) {
+    const int rc = build_window(logn, &win[q], twn, st);
+    guard.track(win[q].d_G); guard.track(win[q].d_R); guard.track_stream(win[q].ramp_stream);
+    if (rc) return -1;
+  }
   clk.mark("window + its spectrum");
 
   // boxcar chains, one stream per filter
@@ -628,10 +657,15 @@ int build_filters(int logn, int count, const FilterSpec *specs, DeviceFilter **o
   // chain wait for the first (measured: 2 x 1.4 s back to back at n = 2^27)
   for (int f = 0; f < count; f++) {
     SFFTB_CUDA(cudaStreamCreateWithFlags(&fs[f], cudaStreamNonBlocking));
+    guard.track_stream(fs[f]);
     SFFTB_CUDA(cudaMalloc(&d_H[f], sizeof(cplx) * n));
+    guard.track(d_H[f]);
     SFFTB_CUDA(cudaMalloc(&d_cand[f], sizeof(cplx) * cand_cap));
+    guard.track(d_cand[f]);
     SFFTB_CUDA(cudaMalloc(&d_maxq[f], sizeof(unsigned long long)));
+    guard.track(d_maxq[f]);
     SFFTB_CUDA(cudaMalloc(&d_ncand[f], sizeof(int)));
+    guard.track(d_ncand[f]);
     SFFTB_CUDA(cudaMalloc(&outs[f]->time, sizeof(cplx) * outs[f]->w));
     SFFTB_CUDA(cudaMalloc(&outs[f]->fwin, sizeof(cplx) * (2ll * specs[f].fw_half + 1)));
   }
@@ -694,6 +728,7 @@ int build_filters(int logn, int count, const FilterSpec *specs, DeviceFilter **o
     // the inverse transform gets its own buffer
     cplx *d_T = nullptr;
     SFFTB_CUDA(cudaMalloc(&d_T, sizeof(cplx) * n));
+    guard.track(d_T);
     normalise_ramp_kernel<<<grid_for(n), kT, 0, fs[f]>>>(d_H[f], ww.d_R, logn, peak, d_T, specs[f].fw_half,
                                                         outs[f]->fwin);
     SFFTB_LAUNCH_CHECK();
@@ -703,6 +738,7 @@ int build_filters(int logn, int count, const FilterSpec *specs, DeviceFilter **o
     if (filter_refresh(outs[f], fs[f])) return -1;
     SFFTB_CUDA(cudaStreamSynchronize(fs[f]));
     cudaFree(d_T);
+    guard.forget(d_T);
   }
   clk.mark("normalise, inverse FFT, taps");
   for (int f = 0; f < count; f++) {
@@ -714,6 +750,7 @@ int build_filters(int logn, int count, const FilterSpec *specs, DeviceFilter **o
     cudaFree(win[q].d_G); cudaFree(win[q].d_R);
   }
   free_twiddles(&twn);
+  guard.dismiss();
   clk.mark("free");
   return 0;
 }
