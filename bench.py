@@ -203,11 +203,30 @@ def _cpu_model():
     return "unknown"
 
 
+def cpu_baseline_leg(workload, nsig):
+    """The cpu_baseline object of the GPU arm's line, taken in a CHILD process: the reference's v3
+    path writes one element past a heap buffer (computefourier-3.0.cc:235) and can abort the
+    process in free(); that must not sink the bench line."""
+    try:
+        env = dict(os.environ, MALLOC_MMAP_THRESHOLD_="32768")
+        out = subprocess.run([sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", workload,
+                              "--steps", "1", "--warmup", "0", "--cpu-leg-signals", str(nsig), "--cpu-leg-budget", "90"],
+                             capture_output=True, text=True, timeout=600, env=env)
+        for ln in reversed(out.stdout.strip().splitlines()):
+            if ln.startswith("{"):
+                d = json.loads(ln)
+                return d.get("cpu_baseline", d)
+        return {"unavailable": "the reference process died (rc %d): %s" % (out.returncode, out.stderr.strip()[-200:])}
+    except Exception as e:     # noqa: BLE001
+        return {"unavailable": repr(e)}
+
+
 def run_reference_arm(args):
     rank = env_int("RANK", 0)
     if rank != 0:
         return
-    r = cpu_reference_run(args.workload, args.gpus * min(BATCH.get(args.workload, 1), 8), args.steps, args.warmup)
+    nsig = args.cpu_leg_signals or args.gpus * min(BATCH.get(args.workload, 1), 8)
+    r = cpu_reference_run(args.workload, nsig, args.steps, args.warmup, budget_s=args.cpu_leg_budget)
     version, n, k, snr_db, desc = WORKLOADS[args.workload]
     if "unavailable" in r:
         print(json.dumps({"impl": "reference", "unavailable": r["unavailable"]}))
@@ -221,7 +240,8 @@ def run_reference_arm(args):
         "config": {"workload": f"{args.workload}: {desc}", "signals_per_step": args.gpus,
                    "n": n, "k": k, "version": version},
         "cpu_baseline": {"value": r["value"], "unit": "Gsamples/s", "cores": r["cores"],
-                         "kind": r["kind"], "sample": r["sample"], "cpu_model": r["cpu_model"]},
+                         "kind": r["kind"], "sample": r["sample"], "cpu_model": r["cpu_model"],
+                         "ms_per_step": r["ms_per_step"], "steps_timed": r["steps_timed"]},
         "e2e": {"value": r["value"], "unit": "Gsamples/s", "h2d_bytes_per_step": 0,
                 "d2h_bytes_per_step": 0},
     }
@@ -704,6 +724,14 @@ def run_ours(args):
                  if stage in traffic else None}
             if notes.get(stage):
                 r["note"] = notes[stage]
+            if stage == "estimate" and version == 2:
+                # floor set by the instruction mix on the measured pipe rates (DESIGN.md K7'): per
+                # recovered coefficient ~640 ALU + 474 FP64 instructions, 2.06 / 2.45 cycles each alone,
+                # 1.5 cycles per instruction when mixed (tools/microbench/pipe_overlap): 6600 cycles per
+                # 512-coefficient tile (its 16 warps sit four to a sub-partition), one tile at a time per SM
+                floor_ms = batch * count / 512.0 / 148 * 6600 / 1.965e9 * 1e3
+                r["instruction_floor_ms"] = floor_ms
+                r["frac_of_instruction_floor"] = floor_ms / ms
             if stage == "gather" and batch == 1:
                 samples = info["gather_samples"] - (info["Comb_loops"] * info["W_Comb"] if version == 2 else 0)
                 rate = samples / (ms * 1e-3)
@@ -751,10 +779,7 @@ def run_ours(args):
                                    "and output copies cannot overlap: the one-way figure is its ceiling; v1/v3 stream "
                                    "the zero fill out while the input streams in (duplex)")
         if world == 1 and not args.no_cpu_baseline:
-            try:
-                line["cpu_baseline"] = cpu_reference_run(args.workload, min(batch, 8), 1, 0, budget_s=90.0)
-            except Exception as e:     # the baseline leg must not sink the bench line
-                line["cpu_baseline"] = {"unavailable": repr(e)}
+            line["cpu_baseline"] = cpu_baseline_leg(args.workload, min(batch, 8))
         print(json.dumps(line))
     plan.close()
     if world > 1:
@@ -769,12 +794,18 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="C2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-leg-signals", type=int, default=0, help=argparse.SUPPRESS)
+    ap.add_argument("--cpu-leg-budget", type=float, default=150.0, help=argparse.SUPPRESS)
     ap.add_argument("--no-extras", action="store_true",
                     help="skip the extra BASELINE configs (C4 loop-sharded, C5 partitioned, C3 replicas)")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3
     if args.impl == "reference":
+        if WORKLOADS[args.workload][0] == 3 and "MALLOC_MMAP_THRESHOLD_" not in os.environ:
+            # the reference's v3 path overruns a heap buffer by one element (computefourier-3.0.cc:235 vs
+            # sfft.cc:497-498): give big allocations their own mappings so the overrun lands in page slack
+            os.execve(sys.executable, [sys.executable] + sys.argv, dict(os.environ, MALLOC_MMAP_THRESHOLD_="32768"))
         run_reference_arm(args)
     else:
         run_ours(args)

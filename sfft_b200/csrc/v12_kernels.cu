@@ -873,7 +873,10 @@ constexpr int kVoteHitCap = 2048;       // hits a CTA collects in shared memory 
 // AGGREGATE: collect the CTA's hits in shared memory and append them with one global atomic
 // (batches: thousands of atomics on one signal's counter serialise in L2); a single signal's
 // short CTAs are better off with direct atomics.
-template <bool SMEM_MAPS, bool AGGREGATE>
+// NLOC = loops_loc at compile time: the bit tests of the other location loops unroll exactly
+// (with a run-time count the eight-way unrolled loop issued every predicated-off test too:
+// ~170 instructions per candidate, the kernel was 83 % issue-bound).
+template <bool SMEM_MAPS, bool AGGREGATE, int NLOC>
 __global__ void __launch_bounds__(kVoteThreads)
 vote_kernel(LoopGeom g, VoteArgs a, int first_loops, int entries_per_cta)
 {
@@ -890,7 +893,7 @@ vote_kernel(LoopGeom g, VoteArgs a, int first_loops, int entries_per_cta)
   const unsigned seg = 1u << logseg, half = seg >> 1;
   const unsigned mask = (unsigned)g.n_mask, Bm = (1u << logB) - 1u;
   const int words = logB >= 5 ? (1 << (logB - 5)) : 1;
-  const int L = g.loops_loc;
+  constexpr int L = NLOC;
   const unsigned *gbm = a.bitmap + (long long)s * a.bm_sig_stride;
   if (SMEM_MAPS)
     for (int i = threadIdx.x; i < L * words; i += kVoteThreads) vote_bm[i] = gbm[i];
@@ -908,10 +911,9 @@ vote_kernel(LoopGeom g, VoteArgs a, int first_loops, int entries_per_cta)
   if (threadIdx.x == 0) s_nhit = 0;
   __syncthreads();
   const unsigned *bm = SMEM_MAPS ? vote_bm : gbm;
-  unsigned ai[kVoteMaxLoops];
+  unsigned ai[L];
 #pragma unroll
-  for (int q = 0; q < kVoteMaxLoops; q++)
-    ai[q] = q < L ? (unsigned)a.perm[(long long)s * perm_stride(g.loops) + g.loops + q] : 0u;
+  for (int q = 0; q < L; q++) ai[q] = (unsigned)a.perm[(long long)s * perm_stride(g.loops) + g.loops + q];
   const unsigned *cb = a.comb_bitmap ? a.comb_bitmap + (long long)s * a.comb_sig_stride : nullptr;
 
   // this CTA's (loop, entry) pairs, flattened with their n/B positions: every thread walks
@@ -930,8 +932,8 @@ vote_kernel(LoopGeom g, VoteArgs a, int first_loops, int entries_per_cta)
     bool earlier = false;
     int score = 1;
 #pragma unroll
-    for (int q = 0; q < kVoteMaxLoops; q++) {
-      if (q < L && q != j) {
+    for (int q = 0; q < L; q++) {
+      if (q != j) {
         const unsigned Jb = ((((ai[q] * loc) & mask) + half) >> logseg) & Bm;
         const bool v = (bm[q * words + (Jb >> 5)] >> (Jb & 31u)) & 1u;
         if (q < j) earlier |= v;
@@ -1023,10 +1025,19 @@ int launch_vote(const LoopGeom &g, const VoteArgs &a, int nsig, cudaStream_t st)
     const dim3 grid((unsigned)blocks, (unsigned)nsig);
     const size_t smem = sizeof(unsigned) * (size_t)g.loops_loc * words;
     const bool maps = smem <= 32 * 1024, agg = nsig > 1;
-    if (maps && agg) vote_kernel<true, true><<<grid, kVoteThreads, smem, st>>>(g, a, first_loops, (int)per_cta);
-    else if (maps) vote_kernel<true, false><<<grid, kVoteThreads, smem, st>>>(g, a, first_loops, (int)per_cta);
-    else if (agg) vote_kernel<false, true><<<grid, kVoteThreads, 0, st>>>(g, a, first_loops, (int)per_cta);
-    else vote_kernel<false, false><<<grid, kVoteThreads, 0, st>>>(g, a, first_loops, (int)per_cta);
+    const size_t dyn = maps ? smem : 0;
+#define SFFTB_VOTE_CASE(N)                                                                                        \
+  case N:                                                                                                         \
+    if (maps && agg) vote_kernel<true, true, N><<<grid, kVoteThreads, dyn, st>>>(g, a, first_loops, (int)per_cta);  \
+    else if (maps) vote_kernel<true, false, N><<<grid, kVoteThreads, dyn, st>>>(g, a, first_loops, (int)per_cta);   \
+    else if (agg) vote_kernel<false, true, N><<<grid, kVoteThreads, dyn, st>>>(g, a, first_loops, (int)per_cta);    \
+    else vote_kernel<false, false, N><<<grid, kVoteThreads, dyn, st>>>(g, a, first_loops, (int)per_cta);            \
+    break;
+    switch (g.loops_loc) {
+      SFFTB_VOTE_CASE(1) SFFTB_VOTE_CASE(2) SFFTB_VOTE_CASE(3) SFFTB_VOTE_CASE(4)
+      SFFTB_VOTE_CASE(5) SFFTB_VOTE_CASE(6) SFFTB_VOTE_CASE(7) SFFTB_VOTE_CASE(8)
+    }
+#undef SFFTB_VOTE_CASE
   }
   SFFTB_LAUNCH_CHECK();
   return 0;

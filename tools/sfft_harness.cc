@@ -38,26 +38,27 @@ static void usage(const char *base)
          "  -h         Print this help message\n", base);
 }
 
-// x[t] = sum_f e^{+2 pi i f t / n} over the k drawn frequencies (collisions allowed)
-static void generate(int n, int k, sfft_complex *x, std::vector<int> &freqs, const std::vector<sfft_complex> &tab)
+// The reference's generator (src/simulation.cc:104-111): k draws f = floor(drand48() * n), X[f] = 1
+// (collisions allowed), x = unnormalised inverse DFT of X.  The inverse DFT runs on the device
+// through the library's stand-alone FFT hook, so BASELINE sizes (n = 2^27) take milliseconds;
+// round 1 summed k complex exponentials per sample, O(n k).
+static int generate(int n, int k, sfft_complex *x, std::vector<int> &freqs)
 {
-  freqs.resize((size_t)k);
-  for (int i = 0; i < k; i++) freqs[(size_t)i] = (int)(unsigned)floor(drand48() * n);
-  std::vector<char> seen((size_t)n, 0);
-  std::vector<int> uniq;
-  for (int i = 0; i < k; i++)
-    if (!seen[(size_t)freqs[(size_t)i]]) { seen[(size_t)freqs[(size_t)i]] = 1; uniq.push_back(freqs[(size_t)i]); }
-  for (int t = 0; t < n; t++) { x[t].re = 0; x[t].im = 0; }
-  for (size_t q = 0; q < uniq.size(); q++) {
-    const unsigned f = (unsigned)uniq[q];
-    unsigned idx = 0;
-    for (int t = 0; t < n; t++) {
-      x[t].re += tab[idx].re;
-      x[t].im += tab[idx].im;
-      idx = (idx + f) & (unsigned)(n - 1);
-    }
+  std::vector<sfft_complex> xf((size_t)n);
+  for (int t = 0; t < n; t++) { xf[(size_t)t].re = 0; xf[(size_t)t].im = 0; }
+  freqs.clear();
+  for (int i = 0; i < k; i++) {
+    const int f = (int)(unsigned)floor(drand48() * n);
+    if (xf[(size_t)f].re == 0) freqs.push_back(f);
+    xf[(size_t)f].re = 1.0;
   }
-  freqs = uniq;
+  int log2n = 0;
+  while ((1 << log2n) < n) log2n++;
+  if (sfftb_debug_fft(xf.data(), x, log2n, 1, +1, 0)) {
+    fprintf(stderr, "input synthesis failed: %s\n", sfftb_last_error());
+    return -1;
+  }
+  return 0;
 }
 
 int main(int argc, char **argv)
@@ -92,14 +93,12 @@ int main(int argc, char **argv)
 
   srand(17);            // src/simulation.cc:100
   srand48(seed);        // deterministic stand-in for time^pid (:101)
-  std::vector<sfft_complex> tab((size_t)n);
-  for (int j = 0; j < n; j++) { tab[(size_t)j].re = cos(2 * M_PI * j / n); tab[(size_t)j].im = sin(2 * M_PI * j / n); }
   std::vector<sfft_complex *> in((size_t)num_inputs), out((size_t)num_inputs);
   std::vector<std::vector<int> > freqs((size_t)num_inputs);
   for (int s = 0; s < num_inputs; s++) {
     in[(size_t)s] = (sfft_complex *)sfft_malloc(sizeof(sfft_complex) * (size_t)n);
     out[(size_t)s] = (sfft_complex *)sfft_malloc(sizeof(sfft_complex) * (size_t)n);
-    generate(n, k, in[(size_t)s], freqs[(size_t)s], tab);
+    if (generate(n, k, in[(size_t)s], freqs[(size_t)s])) return 1;
   }
 
   timespec ts, te;
