@@ -225,7 +225,7 @@ def run_reference_arm(args):
     rank = env_int("RANK", 0)
     if rank != 0:
         return
-    nsig = args.cpu_leg_signals or args.gpus * min(BATCH.get(args.workload, 1), 8)
+    nsig = args.cpu_leg_signals or args.gpus * min(BATCH.get(args.workload, 1), os.cpu_count() or 1)
     r = cpu_reference_run(args.workload, nsig, args.steps, args.warmup, budget_s=args.cpu_leg_budget)
     version, n, k, snr_db, desc = WORKLOADS[args.workload]
     if "unavailable" in r:
@@ -718,7 +718,7 @@ def run_ours(args):
             b = batch * stage_bytes(info, stage, count)
             ach = b / (ms * 1e-3) / 1e9
             r = {"kernel": stage, "bound": "hbm", "achieved": ach, "peak": hbm_peak, "unit": "GB/s",
-                 "frac": ach / hbm_peak, "traffic": (batch * traffic[stage]) if stage in traffic else None,
+                 "frac": ach / hbm_peak, "traffic": traffic[stage] if stage in traffic else None,
                  "ms": ms, "algorithmic_bytes": b, "peak_source": peak_src,
                  "traffic_source": ("ncu dram__bytes_read.sum + dram__bytes_write.sum per launch, " + traffic_file)
                  if stage in traffic else None}
@@ -779,7 +779,7 @@ def run_ours(args):
                                    "and output copies cannot overlap: the one-way figure is its ceiling; v1/v3 stream "
                                    "the zero fill out while the input streams in (duplex)")
         if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_leg(args.workload, min(batch, 8))
+            line["cpu_baseline"] = cpu_baseline_leg(args.workload, min(batch, os.cpu_count() or 1))
         print(json.dumps(line))
     plan.close()
     if world > 1:

@@ -562,7 +562,6 @@ __device__ __forceinline__ int warp_reserve(int *counter, int want)
 // Deterministic whatever the thread timing: targets are grouped by bucket (atomics decide
 // only where a bucket's segment sits and the order INSIDE it), then one thread per touched
 // bucket applies its segment in ascending target id, i.e. in item order.  Four team phases.
-constexpr int kPeelSegLocal = 64;       // peel_apply: segments up to this long are applied out of local memory
 constexpr int kSmallTargets = 2048;     // peel_apply: up to this many targets are handled by CTA 0 in shared memory
 constexpr int kSmallHash = 4096;        // open-addressing table over the touched buckets (load <= 0.5)
 constexpr int kSmallHashShift = 20;     // 32 - log2(kSmallHash)
@@ -576,6 +575,7 @@ struct PeelSmall {
   int hfill[kSmallHash];                // targets counted, then the running fill pointer of the entry's segment
   int hstart[kSmallHash];               // first position of the entry's segment in `order`
   int alloc;                            // segment allocator
+  unsigned char ord[kPeelThreads / 32][64];   // large rounds: per warp, rank -> lane holding that delta
 };
 
 __device__ __forceinline__ int small_find(const PeelSmall &sm, int slot)
@@ -726,41 +726,56 @@ __device__ void peel_apply(const PeelCtx &c, Team &tm, const int *keys, const cp
     if (slot >= 0) seg[atomicAdd(&fill[slot], 1)] = t;
   }
   tm.sync();
-  for (int j = tm.tid; j < T; j += tm.nthreads) {
-    const int sl = touched[j];
-    const int len = cnt[sl];
-    const int *ids = seg + (fill[sl] - len);
-    cplx val = c.samp[sl];
-    int last = -1;
-    if (len <= kPeelSegLocal) {
-      // fetch the segment's deltas with independent loads first: the ordered subtraction then
-      // runs out of local memory instead of paying an L2 round trip per delta
-      int idl[kPeelSegLocal];
-      cplx dl[kPeelSegLocal];
-      for (int q = 0; q < len; q++) idl[q] = ids[q];
-      for (int q = 0; q < len; q++) dl[q] = c.t_delta[idl[q]];
-      for (int rep = 0; rep < len; rep++) {          // ascending target id == item order
-        int best = 0x7fffffff, bq = 0;
-        for (int q = 0; q < len; q++) {
-          const int id = idl[q];
-          if (id > last && id < best) { best = id; bq = q; }
+  // One WARP per touched bucket.  Its lanes fetch the segment's (target id, delta) pairs (two per
+  // lane: up to 64), rank the ids against each other with shuffles, leave "rank -> holder" in
+  // shared memory, and the deltas are then subtracted in ascending id = item order, each fetched
+  // from its holder by one shuffle -- no dependent global loads and no per-thread O(len^2) chain
+  // (one thread per bucket spent ~15 us on the 22-long segments of the 512 permuted-window slots).
+  {
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+    unsigned char *ord = sm.ord[wib];
+    for (int j = tm.tid >> 5; j < T; j += tm.nthreads >> 5) {
+      const int sl = touched[j];
+      const int len = cnt[sl];
+      const int *ids = seg + (fill[sl] - len);
+      cplx val = c.samp[sl];
+      if (len <= 64) {
+        const int id0 = lane < len ? ids[lane] : 0x7fffffff;
+        const int id1 = lane + 32 < len ? ids[lane + 32] : 0x7fffffff;
+        const cplx zero = make_double2(0.0, 0.0);
+        const cplx d0 = lane < len ? c.t_delta[id0] : zero;
+        const cplx d1 = lane + 32 < len ? c.t_delta[id1] : zero;
+        int r0 = 0, r1 = 0;
+        for (int q = 0; q < 32; q++) {
+          const int o0 = __shfl_sync(0xffffffffu, id0, q), o1 = __shfl_sync(0xffffffffu, id1, q);
+          r0 += (o0 < id0) + (o1 < id0);
+          r1 += (o0 < id1) + (o1 < id1);
         }
-        val = csub_rn(val, dl[bq]);
-        last = best;
-      }
-    } else {
-      for (int rep = 0; rep < len; rep++) {
-        int best = 0x7fffffff;
-        for (int q = 0; q < len; q++) {
-          const int id = ids[q];
-          if (id > last && id < best) best = id;
+        if (lane < len) ord[r0] = (unsigned char)lane;
+        if (lane + 32 < len) ord[r1] = (unsigned char)(lane + 32);
+        __syncwarp();
+        for (int r = 0; r < len; r++) {              // ascending target id == item order
+          const int holder = ord[r];
+          const cplx mine = holder >= 32 ? d1 : d0;
+          const cplx d = make_double2(__shfl_sync(0xffffffffu, mine.x, holder & 31),
+                                      __shfl_sync(0xffffffffu, mine.y, holder & 31));
+          val = csub_rn(val, d);
         }
-        val = csub_rn(val, c.t_delta[best]);
-        last = best;
+        __syncwarp();
+      } else {
+        int last = -1;
+        for (int rep = 0; rep < len; rep++) {
+          int best = 0x7fffffff;
+          for (int q = 0; q < len; q++) {
+            const int id = ids[q];
+            if (id > last && id < best) best = id;
+          }
+          val = csub_rn(val, c.t_delta[best]);
+          last = best;
+        }
       }
+      if (lane == 0) { c.samp[sl] = val; cnt[sl] = 0; }
     }
-    c.samp[sl] = val;
-    cnt[sl] = 0;
   }
   if (tm.tid == 0) { *ntouched = 0; *seg_alloc = 0; }
   tm.sync();
