@@ -194,7 +194,7 @@ __global__ void v3_gauss_perm_kernel(V3Geom g, const cplx *__restrict__ x_direct
 }
 
 // ---- the peeling loop ------------------------------------------------------
-constexpr int kPeelThreads = 1024;
+constexpr int kPeelThreads = 512;
 
 struct PeelArgs {
   const int *draw;
@@ -276,7 +276,7 @@ __device__ int block_scan_excl(int v, int &total, unsigned *warp_tot)
   if (lane == 31) warp_tot[warp] = (unsigned)incl;
   __syncthreads();
   if (warp == 0) {
-    const int t = (int)warp_tot[lane];
+    const int t = lane < (int)(blockDim.x >> 5) ? (int)warp_tot[lane] : 0;      // CTAs of fewer than 32 warps
     int sc = t;
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
@@ -1137,7 +1137,7 @@ int v3_build(PlanImpl *p, int n_req, int k)
   // CTAs per signal in the peeling kernel: one SM per 1024 aliasing buckets, at most a
   // 16-CTA cluster (non-portable size; 8 if the device will not schedule 16)
   v.team = 1;
-  while (v.team < kMaxTeam && v.team * 1024 < v.W_Man) v.team <<= 1;
+  while (v.team < kMaxTeam && v.team * kPeelThreads < v.W_Man) v.team <<= 1;
   if (const char *e = getenv("SFFTB_V3_TEAM")) {
     const int t = atoi(e);
     if (t == 1 || t == 2 || t == 4 || t == 8 || t == 16) v.team = t;
