@@ -103,6 +103,11 @@ struct PlanV12 {
   int plain_execs = 0;
   int graph_kernels = 0;                   // kernels in one transform (for the launch counter)
   long long *h_counts = nullptr;   // pinned
+  // plans whose location and estimation rows differ in size: the estimation rows' FFT runs on a
+  // side stream, under the location rows' FFT + selection + voting (joined before estimation)
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t side_fork = nullptr, side_join = nullptr;
+  bool side_pending = false;
   ShardPeers shard;
 };
 

@@ -193,6 +193,11 @@ int v12_build(PlanImpl *p)
   }
   v.ints_per_sig = 2 * v.geom.loops + v.Comb_loops;
   for (int i = 0; i < kStageSlots; i++) SFFTB_CUDA(cudaEventCreateWithFlags(&v.stage_ev[i], cudaEventDisableTiming));
+  if (v.B_loc != v.B_est && !v.with_comb) {
+    SFFTB_CUDA(cudaStreamCreateWithFlags(&v.side_stream, cudaStreamNonBlocking));
+    SFFTB_CUDA(cudaEventCreateWithFlags(&v.side_fork, cudaEventDisableTiming));
+    SFFTB_CUDA(cudaEventCreateWithFlags(&v.side_join, cudaEventDisableTiming));
+  }
   return v12_ensure_capacity(p, 1);
 }
 
@@ -306,6 +311,10 @@ void v12_free(PlanImpl *p)
     if (v.stage_ev[i]) cudaEventDestroy(v.stage_ev[i]);
     v.stage_ev[i] = nullptr;
   }
+  if (v.side_stream) cudaStreamDestroy(v.side_stream);
+  if (v.side_fork) cudaEventDestroy(v.side_fork);
+  if (v.side_join) cudaEventDestroy(v.side_join);
+  v.side_stream = nullptr; v.side_fork = nullptr; v.side_join = nullptr;
 }
 
 // One transform's worth of libc randomness, in the reference's order:
@@ -408,14 +417,37 @@ static int v12_stage_bucketize(PlanImpl *p, const cplx *d_in, const unsigned lon
     if (fft_dit_inplace(v.d_xs + (long long)lb * v.B_loc, g.logB[0], le - lb, v.B_loc, nsig,
                         v.x_samp_size, v.d_tw, v.log_twN, -1, st)) return -1;
   } else {
+    // the estimation rows are not needed before the estimation stage: fork their FFT onto the
+    // side stream (a parallel branch of the captured graph) and join in v12_stage_finish
+    cudaStream_t est_st = st;
+    if (est_e > est_b && loc_e > loc_b && v.side_stream && !p->timer.enabled) {
+      SFFTB_CUDA(cudaEventRecord(v.side_fork, st));
+      SFFTB_CUDA(cudaStreamWaitEvent(v.side_stream, v.side_fork, 0));
+      est_st = v.side_stream;
+    }
+    if (est_e > est_b &&
+        fft_dit_inplace(v.d_xs + (long long)v.loops_loc * v.B_loc + (long long)est_b * v.B_est, g.logB[1],
+                        est_e - est_b, v.B_est, nsig, v.x_samp_size, v.d_tw, v.log_twN, -1, est_st)) return -1;
+    if (est_st != st) {
+      SFFTB_CUDA(cudaEventRecord(v.side_join, est_st));
+      v.side_pending = true;
+    }
     if (loc_e > loc_b &&
         fft_dit_inplace(v.d_xs + (long long)loc_b * v.B_loc, g.logB[0], loc_e - loc_b, v.B_loc, nsig,
                         v.x_samp_size, v.d_tw, v.log_twN, -1, st)) return -1;
-    if (est_e > est_b &&
-        fft_dit_inplace(v.d_xs + (long long)v.loops_loc * v.B_loc + (long long)est_b * v.B_est, g.logB[1],
-                        est_e - est_b, v.B_est, nsig, v.x_samp_size, v.d_tw, v.log_twN, -1, st)) return -1;
   }
   timer_mark(p, "bucket_fft");
+  return 0;
+}
+
+// make the main stream wait for the estimation rows' FFT if it was forked onto the side stream
+static int v12_join_side(PlanImpl *p)
+{
+  PlanV12 &v = p->v12;
+  if (v.side_pending) {
+    SFFTB_CUDA(cudaStreamWaitEvent(p->stream, v.side_join, 0));
+    v.side_pending = false;
+  }
   return 0;
 }
 
@@ -484,6 +516,7 @@ static int v12_stage_finish(PlanImpl *p, int nsig, int slice_rank, int slice_wor
   } else if (v12_stage_locate(p, nsig)) {
     return -1;
   }
+  if (v12_join_side(p)) return -1;       // the estimation rows' FFT ran beside selection and voting
 
   EstimateArgs ea;
   ea.perm = d_perm;
@@ -628,7 +661,8 @@ int v12_shard_bucketize(PlanImpl *p, const cplx *d_in, const sfftb_draw *draw, i
   SFFTB_CUDA(cudaMemsetAsync(v.d_xs, 0, sizeof(cplx) * v.x_samp_size, p->stream));
   int lb, le;
   v12_shard_loops(p, rank, world, &lb, &le);
-  return v12_stage_bucketize(p, d_in, nullptr, p->n, 1, lb, le);
+  if (v12_stage_bucketize(p, d_in, nullptr, p->n, 1, lb, le)) return -1;
+  return v12_join_side(p);               // the caller's collective follows on the plan's stream
 }
 
 int v12_shard_finish(PlanImpl *p, int rank, int world) { return v12_stage_finish(p, 1, rank, world); }
@@ -642,6 +676,7 @@ static int v12_shard_body(PlanImpl *p, const cplx *d_in, const unsigned long lon
   v12_shard_loops(p, sh.rank, sh.world, &lb, &le);
   if (v12_stage_comb(p, d_in, x_ind, p->n, 1)) return -1;              // tiny; replicated on every rank
   if (v12_stage_bucketize(p, d_in, x_ind, p->n, 1, lb, le)) return -1;
+  if (v12_join_side(p)) return -1;       // every owned row must be complete before it is stored into the peers
   // rows of loops [lb, le) are one contiguous block of the spectra buffer (cf12.cc:228-230)
   const long long off = lb < v.loops_loc ? (long long)lb * v.B_loc
                                          : (long long)v.loops_loc * v.B_loc + (long long)(lb - v.loops_loc) * v.B_est;
