@@ -1014,10 +1014,10 @@ int launch_vote(const LoopGeom &g, const VoteArgs &a, int nsig, cudaStream_t st)
     vote_generic_kernel<<<dim3((unsigned)blocks, (unsigned)nsig), kVoteThreads, 0, st>>>(g, a, first_loops);
   } else {
     // voting is latency-bound per CTA: as many CTAs as there are entries, until the grid is a
-    // few waves deep; beyond that (batches) a CTA takes up to 4096 candidates' worth of entries
+    // few waves deep; beyond that (batches) a CTA takes up to 8192 candidates' worth of entries
     const int logseg = g.logn - g.logB[0];
     long long per_cta = entries * nsig / 600;
-    long long most = logseg >= 12 ? 1 : (4096 >> logseg);
+    long long most = logseg >= 12 ? 1 : (8192 >> logseg);
     if (most > kVoteMaxEntries) most = kVoteMaxEntries;
     if (per_cta > most) per_cta = most;
     if (per_cta < 1) per_cta = 1;
