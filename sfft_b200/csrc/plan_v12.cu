@@ -193,7 +193,7 @@ int v12_build(PlanImpl *p)
   }
   v.ints_per_sig = 2 * v.geom.loops + v.Comb_loops;
   for (int i = 0; i < kStageSlots; i++) SFFTB_CUDA(cudaEventCreateWithFlags(&v.stage_ev[i], cudaEventDisableTiming));
-  if (v.B_loc != v.B_est && !v.with_comb) {
+  if (v.B_loc != v.B_est || v.with_comb) {
     SFFTB_CUDA(cudaStreamCreateWithFlags(&v.side_stream, cudaStreamNonBlocking));
     SFFTB_CUDA(cudaEventCreateWithFlags(&v.side_fork, cudaEventDisableTiming));
     SFFTB_CUDA(cudaEventCreateWithFlags(&v.side_join, cudaEventDisableTiming));
@@ -370,8 +370,17 @@ static int v12_stage_draws(PlanImpl *p, int nsig, const sfftb_draw *draws)
 static int v12_stage_comb(PlanImpl *p, const cplx *d_in, const unsigned long long *x_ind, long long stride, int nsig)
 {
   PlanV12 &v = p->v12;
-  cudaStream_t st = p->stream;
   if (!v.with_comb) return 0;
+  // The Comb filter and the gather + bucket FFTs are independent until estimation: the Comb's four
+  // small kernels (~38 us of latency) run on the side stream, under the gather (a parallel branch
+  // of the captured graph); v12_join_side brings them back before estimation.
+  cudaStream_t st = p->stream;
+  const bool forked = v.side_stream && !p->timer.enabled;
+  if (forked) {
+    SFFTB_CUDA(cudaEventRecord(v.side_fork, p->stream));        // after the draws have been queued
+    SFFTB_CUDA(cudaStreamWaitEvent(v.side_stream, v.side_fork, 0));
+    st = v.side_stream;
+  }
   const int num = v.B_thresh, loops = v.geom.loops;
   const int *d_coff = v.d_stage + (long long)nsig * 2 * loops;
   const int W = v.W_Comb, logW = ilog2((unsigned)W), words = W >= 32 ? W / 32 : 1;
@@ -390,6 +399,10 @@ static int v12_stage_comb(PlanImpl *p, const cplx *d_in, const unsigned long lon
   if (launch_select(sa, v.Comb_loops, nsig, st)) return -1;
   if (launch_comb_merge(v.d_comb_bm, v.Comb_loops, W, p->n / W, v.d_appr_bm, v.d_approved,
                         v.d_num_comb, v.d_count, nsig, st)) return -1;
+  if (forked) {
+    SFFTB_CUDA(cudaEventRecord(v.side_join, st));
+    v.side_pending = true;
+  }
   timer_mark(p, "comb");
   return 0;
 }
