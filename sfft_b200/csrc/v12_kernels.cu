@@ -1426,6 +1426,30 @@ __device__ __forceinline__ bool v2_band_or_zero(double x)
 
 constexpr int kV2Chunk = 4;           // tiles claimed per atomic
 
+// v[(L-1)/2] of the ascending order of v, selected on 32-bit keys.  The high word of a double,
+// read as a float, orders like the double itself (sign, then exponent and leading mantissa
+// bits) as long as it is neither a float NaN/Inf/subnormal pattern nor -0 -- true for every
+// quotient of a tile whose inputs are in the proven band (div_fast above: |q| in
+// [2^-758, 2^766) or +0).  The network then costs one FMNMX per min / max instead of one
+// 64-bit compare and two selects per live word.  The key of the median is its high word; the
+// low word is picked up from the one quotient carrying that high word.  When several do (they
+// agree to 2^-20: the loops' estimates of a real coefficient), or when the tile is outside the
+// band, the exact 64-bit network decides -- v is untouched until then.
+template <int L>
+__device__ __forceinline__ double v2_median(double (&v)[L], int exact)
+{
+  float key[L];
+#pragma unroll
+  for (int j = 0; j < L; j++) key[j] = __int_as_float(__double2hiint(v[j]));
+  const int mh = __float_as_int(MedianNet<L>::run_hi(key));
+  unsigned lo = 0u, cnt = 0u;
+#pragma unroll
+  for (int j = 0; j < L; j++)
+    if (__double2hiint(v[j]) == mh) { lo = (unsigned)__double2loint(v[j]); cnt++; }
+  if (exact | (cnt != 1u)) return MedianNet<L>::run(v);
+  return __hiloint2double(mh, (int)lo);
+}
+
 __device__ __forceinline__ void mbar_arrive(unsigned bar)
 {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
@@ -1594,8 +1618,8 @@ v2_fused_kernel(LoopGeom g, V2StructArgs a)
     }
     parity ^= 1u;
 
-    const double re = MedianNet<L>::run(vr);
-    const double im = MedianNet<L>::run(vi);
+    const double re = v2_median<L>(vr, unsafe);
+    const double im = v2_median<L>(vi, unsafe);
     const unsigned c = (unsigned)(tile & ((1ll << sbits) - 1));
     const unsigned jj = c + (u << sbits);
     const long long o = (long long)sig * a.out_cap + ((tile - lo) << logT) + u;

@@ -207,7 +207,9 @@ def main(out_path=OUT):
              "(a) = s_ ? y_ : x_; (b) = s_ ? x_ : y_; }\n",
              "#define SFFTB_MIN(a, b) ((b) < (a) ? (b) : (a))\n",
              "#define SFFTB_MAX(a, b) ((b) < (a) ? (a) : (b))\n",
-             "template <int K> struct IntC { static constexpr int value = K; };\n",
+             "// run_hi: the same network on 32-bit keys (the doubles' high words read as floats: one\n",
+             "// FMNMX per min / max instead of a 64-bit compare and two selects per output).\n",
+             "#define SFFTB_FCSWAP(a, b) { const float x_ = (a), y_ = (b); (a) = fminf(x_, y_); (b) = fmaxf(x_, y_); }\n",
              "template <int L> struct MedianNet;\n"]
     for n in range(LMIN, LMAX + 1):
         a = construction_a(n)
@@ -230,30 +232,22 @@ def main(out_path=OUT):
                     declared.add(op[1]); decl = "const double "
                 lines.append(f"    {decl}{d} = {macro}({name(op[2], n)}, {name(op[3], n)});\n")
         lines.append(f"    return {name(want, n)};\n  }}\n")
-        # same network with L evenly spaced hooks: side(IntC<k>) runs between its operations, so
-        # independent work (FP64 divisions) can be interleaved with the ALU-bound selects
-        lines.append(f"  template <class F> static __device__ __forceinline__ double run_with(double (&v)[{n}], F &&side) {{\n")
+        # the same operations on float keys
+        lines.append(f"  static __device__ __forceinline__ float run_hi(float (&v)[{n}]) {{\n")
         declared = set()
-        hooks = 0
-        for t, op in enumerate(ops):
-            while hooks < n and hooks * len(ops) <= t * n:
-                lines.append(f"    side(IntC<{hooks}>());\n")
-                hooks += 1
+        for op in ops:
             if op[0] == "cs":
-                lines.append(f"    SFFTB_CSWAP({name(op[1], n)}, {name(op[2], n)})\n")
+                lines.append(f"    SFFTB_FCSWAP({name(op[1], n)}, {name(op[2], n)})\n")
             else:
                 d = name(op[1], n)
-                macro = "SFFTB_MIN" if op[0] == "min" else "SFFTB_MAX"
+                fn = "fminf" if op[0] == "min" else "fmaxf"
                 decl = ""
                 if op[1] >= n and op[1] not in declared:
-                    declared.add(op[1]); decl = "const double "
-                lines.append(f"    {decl}{d} = {macro}({name(op[2], n)}, {name(op[3], n)});\n")
-        while hooks < n:
-            lines.append(f"    side(IntC<{hooks}>());\n")
-            hooks += 1
+                    declared.add(op[1]); decl = "const float "
+                lines.append(f"    {decl}{d} = {fn}({name(op[2], n)}, {name(op[3], n)});\n")
         lines.append(f"    return {name(want, n)};\n  }}\n}};\n")
         print(n, tag, "compares", compares, "selects", selects, "| A", a[2], a[1], "| B", b[2], b[1])
-    lines.append("#undef SFFTB_CSWAP\n#undef SFFTB_MIN\n#undef SFFTB_MAX\n")
+    lines.append("#undef SFFTB_CSWAP\n#undef SFFTB_FCSWAP\n#undef SFFTB_MIN\n#undef SFFTB_MAX\n")
     open(out_path, "w").writelines(lines)
 
 
