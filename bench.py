@@ -697,9 +697,11 @@ def run_ours(args):
                 pass
         notes = {
             "estimate": ("v2_regroup_kernel + v2_fused_kernel: DRAM traffic equals the algorithmic bytes (spectra in, "
-                         "result list out); bound by instruction issue on the ALU select pipe (two medians of 20: 540 "
-                         "FSEL + 154 DSETP per coefficient) and the FP64 pipe (40 exact divisions): 76 % of the floor "
-                         "those pipes set for this instruction mix -- DESIGN.md K7', profiles/r02_C2_full.txt, "
+                         "result list out); bound by instruction issue: per coefficient ~410 ALU-pipe instructions (two "
+                         "medians of 20 selected on 32-bit keys: 258 FMNMX + recovery of the low word) and 320 FP64 ones "
+                         "(40 exact divisions), which the 16 warps of a tile execute in two separate phases -- ncu: ALU "
+                         "pipe 44 %, FP64 pipe 35 %, shared-memory wavefronts 40 % busy, no eligible warp in 49 % of the "
+                         "cycles -- DESIGN.md K7', profiles/r02_v2_fused_keymedian_ncu_details.txt, "
                          "profiles/r02_pipe_overlap.jsonl") if version == 2 else None,
             "gather": ("bound by the random-REQUEST rate of HBM, not its bandwidth: 16-byte samples at a random odd "
                        "stride, one per 32-byte sector (sector efficiency 50 % on the signal stream, the ceiling); "
@@ -726,10 +728,10 @@ def run_ours(args):
                 r["note"] = notes[stage]
             if stage == "estimate" and version == 2:
                 # floor set by the instruction mix on the measured pipe rates (DESIGN.md K7'): per
-                # recovered coefficient ~640 ALU + 474 FP64 instructions, 2.06 / 2.45 cycles each alone,
-                # 1.5 cycles per instruction when mixed (tools/microbench/pipe_overlap): 6600 cycles per
+                # recovered coefficient ~410 ALU + 320 FP64 instructions, 2.06 / 2.45 cycles each alone,
+                # 1.5 cycles per instruction when mixed (tools/microbench/pipe_overlap): 4330 cycles per
                 # 512-coefficient tile (its 16 warps sit four to a sub-partition), one tile at a time per SM
-                floor_ms = batch * count / 512.0 / 148 * 6600 / 1.965e9 * 1e3
+                floor_ms = batch * count / 512.0 / 148 * 4330 / 1.965e9 * 1e3
                 r["instruction_floor_ms"] = floor_ms
                 r["frac_of_instruction_floor"] = floor_ms / ms
             if stage == "gather" and batch == 1:
