@@ -21,6 +21,8 @@ print("# per kernel: opcode histogram (top 14) and the instructions that show th
 print("#   UBLKCP = cp.async.bulk (TMA engine), SYNCS = mbarrier, UCGABAR_* = barrier.cluster, LDG...LTC64B = .L2::64B fills,")
 print("#   ATOMS/REDS/MAPA = shared-memory atomics incl. distributed shared memory, *.SYS + MEMBAR.*.SYS = the peer-memory")
 print("#   protocol of the sharded transform (stores into CUDA-IPC-mapped peer buffers, flags with release/acquire at system scope)")
+print("#   v2_fused_kernel: FMNMX/FMNMX3 = the medians on 32-bit keys (hot path); its FSEL/DSETP are the exact 64-bit networks of the")
+print("#   tie / out-of-band fallback (cold)")
 print()
 for obj, kerns in OBJS.items():
     sass = subprocess.run(["cuobjdump", "-sass", "sfft_b200/build/" + obj], capture_output=True, text=True).stdout
